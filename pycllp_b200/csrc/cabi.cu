@@ -1,0 +1,457 @@
+// cabi.cu -- the C ABI declared in include/pycllp_b200.h (engine object, setup-time
+// analysis of the shared matrix, host/device solve entry points, test hooks).
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/pycllp_b200.h"
+#include "ipm_types.h"
+#include "ipm_host.h"
+
+using namespace pb200;
+
+static thread_local std::string g_create_error;
+
+struct pycllp_b200_engine {
+  int device = 0, num_sms = 0;
+  size_t smem_optin = 0;
+  std::string err;
+  bool ready = false;
+  Matrix A{};
+  Params p{};
+  Scratch sc{};
+  std::vector<void*> matrix_allocs;   // freed on re-setup / destroy
+  int grid = 0, max_problems = 0;
+  size_t smem_bytes = 0;
+  // staging buffers of the host-buffer entry points
+  double *d_b = nullptr, *d_c = nullptr, *d_x = nullptr, *d_y = nullptr, *d_z = nullptr;
+  int *d_status = nullptr, *d_iters = nullptr;
+  cudaStream_t stream = nullptr;
+  long long launches = 0;
+};
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    int cur;
+    cudaGetDevice(&cur);
+    if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+int fail(pycllp_b200_engine* e, int code, const std::string& msg) {
+  if (e) e->err = msg;
+  return code;
+}
+
+#define CU(call)                                                                         \
+  do {                                                                                   \
+    cudaError_t _err = (call);                                                           \
+    if (_err != cudaSuccess)                                                             \
+      return fail(e, PYCLLP_B200_ERR_CUDA,                                               \
+                  std::string(#call) + ": " + cudaGetErrorString(_err));                 \
+  } while (0)
+
+void default_params(Params& p, bool sparse) {
+  p.eps = (double)1.0e-7f;      // primal_normal.cl:8 -- a float literal
+  p.delta = 0.02;               // :10
+  p.r = 0.9;                    // :11
+  p.ldl_delta = 1e-6;           // :275
+  p.refine_tol = 1e-8;          // ldl.cl:645
+  p.max_iter = 200;             // primal_normal.cl:9
+  p.max_refine = sparse ? 0 : 5;  // ldl.cl:645 / ldl.cl:698-711 (commented out)
+}
+
+template <class T>
+int upload(pycllp_b200_engine* e, const std::vector<T>& h, const T** out) {
+  T* d = nullptr;
+  size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(T);
+  CU(cudaMalloc(&d, bytes));
+  e->matrix_allocs.push_back(d);
+  if (!h.empty()) CU(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  *out = d;
+  return 0;
+}
+
+void free_matrix(pycllp_b200_engine* e) {
+  for (void* p : e->matrix_allocs) cudaFree(p);
+  e->matrix_allocs.clear();
+  void* bufs[] = {e->d_b, e->d_c, e->d_x, e->d_y, e->d_z, e->d_status, e->d_iters};
+  for (void* p : bufs)
+    if (p) cudaFree(p);
+  e->d_b = e->d_c = e->d_x = e->d_y = e->d_z = nullptr;
+  e->d_status = e->d_iters = nullptr;
+  e->ready = false;
+}
+
+size_t al16(size_t v) { return (v + 15) & ~(size_t)15; }
+
+// choose the shared-memory configuration, the grid and allocate scratch + staging
+int finish_setup(pycllp_b200_engine* e, int max_problems) {
+  const int m = e->A.m, n = e->A.n;
+  const size_t limit = e->smem_optin - 1024;   // static smem + margin
+  int Ls = 1, Vs = 1;
+  if (smem_doubles(e->A, 1, 1) * 8 > limit) { Ls = 0; }
+  if (smem_doubles(e->A, Ls, 1) * 8 > limit) { Vs = 0; }
+  if (smem_doubles(e->A, Ls, Vs) * 8 > limit)
+    return fail(e, PYCLLP_B200_ERR_ARG, "problem too large for the shared-memory work area");
+  e->smem_bytes = smem_doubles(e->A, Ls, Vs) * 8;
+  const size_t lsz = (size_t)m * (m + 1) / 2;
+  size_t slot = al16((size_t)m * m);
+  e->sc.off_L = slot;
+  if (!Ls) slot += al16(lsz);
+  e->sc.off_vec = slot;
+  if (!Vs) slot += al16((size_t)6 * n + 6 * m);
+  e->sc.slot = slot;
+  e->sc.L_in_smem = Ls;
+  e->sc.vec_in_smem = Vs;
+  int per_sm = solve_kernel_max_blocks_per_sm(e->smem_bytes);
+  if (per_sm < 1) return fail(e, PYCLLP_B200_ERR_CUDA, "kernel does not fit on an SM");
+  e->grid = std::max(1, std::min(max_problems, e->num_sms * per_sm));
+  e->max_problems = max_problems;
+  double* base = nullptr;
+  CU(cudaMalloc(&base, slot * sizeof(double) * e->grid));
+  e->matrix_allocs.push_back(base);
+  e->sc.base = base;
+  int* counter = nullptr;
+  CU(cudaMalloc(&counter, sizeof(int)));
+  e->matrix_allocs.push_back(counter);
+  e->sc.counter = counter;
+  const size_t N = (size_t)max_problems;
+  CU(cudaMalloc(&e->d_b, N * m * sizeof(double)));
+  CU(cudaMalloc(&e->d_c, N * n * sizeof(double)));
+  CU(cudaMalloc(&e->d_x, N * n * sizeof(double)));
+  CU(cudaMalloc(&e->d_y, N * m * sizeof(double)));
+  CU(cudaMalloc(&e->d_z, N * n * sizeof(double)));
+  CU(cudaMalloc(&e->d_status, N * sizeof(int)));
+  CU(cudaMalloc(&e->d_iters, N * sizeof(int)));
+  e->ready = true;
+  return 0;
+}
+
+int run(pycllp_b200_engine* e, Batch& B, cudaStream_t stream) {
+  CU(cudaMemsetAsync(e->sc.counter, 0, sizeof(int), stream));
+  int grid = std::min(e->grid, std::max(1, B.N));
+  CU(launch_solve(e->A, B, e->sc, e->p, grid, e->smem_bytes, stream));
+  e->launches += 1;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* pycllp_b200_version(void) { return "pycllp_b200 0.1 (sm_100a)"; }
+
+const char* pycllp_b200_last_error(const pycllp_b200_engine* e) {
+  return e ? e->err.c_str() : g_create_error.c_str();
+}
+
+int pycllp_b200_create(int device, pycllp_b200_engine** out) {
+  if (!out) return PYCLLP_B200_ERR_ARG;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t err = cudaGetDeviceCount(&count);
+  if (err != cudaSuccess || count == 0) {
+    g_create_error = std::string("no usable CUDA device: ") +
+                     (err != cudaSuccess ? cudaGetErrorString(err) : "device count is 0") +
+                     " (this engine has no CPU fallback)";
+    return PYCLLP_B200_ERR_CUDA;
+  }
+  if (device < 0 || device >= count) {
+    g_create_error = "device index out of range";
+    return PYCLLP_B200_ERR_ARG;
+  }
+  pycllp_b200_engine* e = new pycllp_b200_engine();
+  e->device = device;
+  DeviceGuard guard(device);
+  cudaDeviceProp prop;
+  err = cudaGetDeviceProperties(&prop, device);
+  if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+  if (err != cudaSuccess) {
+    g_create_error = cudaGetErrorString(err);
+    delete e;
+    return PYCLLP_B200_ERR_CUDA;
+  }
+  e->num_sms = prop.multiProcessorCount;
+  e->smem_optin = prop.sharedMemPerBlockOptin;
+  default_params(e->p, false);
+  *out = e;
+  return 0;
+}
+
+int pycllp_b200_destroy(pycllp_b200_engine* e) {
+  if (!e) return 0;
+  {
+    DeviceGuard guard(e->device);
+    cudaDeviceSynchronize();
+    free_matrix(e);
+    if (e->stream) cudaStreamDestroy(e->stream);
+  }
+  delete e;
+  return 0;
+}
+
+int pycllp_b200_setup_dense(pycllp_b200_engine* e, int m, int n, const double* A,
+                            int max_problems) {
+  if (!e || !A || m <= 0 || n <= 0 || max_problems <= 0)
+    return fail(e, PYCLLP_B200_ERR_ARG, "setup_dense: bad argument");
+  DeviceGuard guard(e->device);
+  free_matrix(e);
+  Matrix& M = e->A;
+  M = Matrix{};
+  M.m = m; M.n = n; M.sparse = 0;
+  default_params(e->p, false);
+  // classify columns by their number of non-zeros
+  std::vector<int> cnt(n, 0), one_row(n, -1);
+  for (int i = 0; i < m; i++)
+    for (int j = 0; j < n; j++)
+      if (A[(size_t)i * n + j] != 0.0) { cnt[j]++; one_row[j] = i; }
+  std::vector<int> dcols;
+  std::vector<std::vector<std::pair<int, double>>> sing(m);
+  for (int j = 0; j < n; j++) {
+    if (cnt[j] >= 2) dcols.push_back(j);
+    else if (cnt[j] == 1) {
+      double a = A[(size_t)one_row[j] * n + j];
+      sing[one_row[j]].push_back({j, a * a});
+    }
+  }
+  M.nd = (int)dcols.size();
+  M.ldd = std::max(KC, (M.nd + KC - 1) / KC * KC);
+  std::vector<double> Ad((size_t)m * M.ldd, 0.0);
+  for (int i = 0; i < m; i++)
+    for (int k = 0; k < M.nd; k++) Ad[(size_t)i * M.ldd + k] = A[(size_t)i * n + dcols[k]];
+  dcols.resize(M.ldd, 0);
+  std::vector<int> sptr(m + 1, 0), scol;
+  std::vector<double> sw;
+  for (int i = 0; i < m; i++) {
+    for (auto& pr : sing[i]) { scol.push_back(pr.first); sw.push_back(pr.second); }
+    sptr[i + 1] = (int)scol.size();
+  }
+  std::vector<double> Ah(A, A + (size_t)m * n);
+  int rc;
+  if ((rc = upload(e, Ah, &M.A))) return rc;
+  if ((rc = upload(e, Ad, &M.Ad))) return rc;
+  if ((rc = upload(e, dcols, &M.dcols))) return rc;
+  if ((rc = upload(e, sptr, &M.sing_ptr))) return rc;
+  if ((rc = upload(e, scol, &M.sing_col))) return rc;
+  if ((rc = upload(e, sw, &M.sing_w))) return rc;
+  return finish_setup(e, max_problems);
+}
+
+int pycllp_b200_setup_sparse(pycllp_b200_engine* e, int m, int n, const int* indptr,
+                             const int* indices, const double* data, int max_problems) {
+  if (!e || !indptr || !indices || !data || m <= 0 || n <= 0 || max_problems <= 0)
+    return fail(e, PYCLLP_B200_ERR_ARG, "setup_sparse: bad argument");
+  DeviceGuard guard(e->device);
+  free_matrix(e);
+  Matrix& M = e->A;
+  M = Matrix{};
+  M.m = m; M.n = n; M.sparse = 1;
+  default_params(e->p, true);
+  const int nnz = indptr[m];
+  for (int k = 0; k < nnz; k++)
+    if (indices[k] < 0 || indices[k] >= n)
+      return fail(e, PYCLLP_B200_ERR_ARG, "setup_sparse: column index out of range");
+  std::vector<int> Ap(indptr, indptr + m + 1), Ai(indices, indices + nnz);
+  std::vector<double> Ax(data, data + nnz);
+  // CSR of A' (= CSC of A), rows ascending inside each column
+  std::vector<int> Tp(n + 1, 0), Ti(nnz);
+  std::vector<double> Tx(nnz);
+  for (int k = 0; k < nnz; k++) Tp[Ai[k] + 1]++;
+  for (int j = 0; j < n; j++) Tp[j + 1] += Tp[j];
+  {
+    std::vector<int> pos(Tp.begin(), Tp.end() - 1);
+    for (int i = 0; i < m; i++)
+      for (int k = Ap[i]; k < Ap[i + 1]; k++) {
+        int d = pos[Ai[k]]++;
+        Ti[d] = i;
+        Tx[d] = Ax[k];
+      }
+  }
+  // symbolic analysis of M = A diag(d) A' (shared pattern): triples (i >= j, k, A_ik A_jk)
+  struct Tr { int i, j, k; double w; };
+  std::vector<Tr> tr;
+  for (int k = 0; k < n; k++)
+    for (int a = Tp[k]; a < Tp[k + 1]; a++)
+      for (int b2 = Tp[k]; b2 <= a; b2++)
+        tr.push_back({Ti[a], Ti[b2], k, Tx[a] * Tx[b2]});
+  std::sort(tr.begin(), tr.end(), [](const Tr& u, const Tr& v) {
+    if (u.i != v.i) return u.i < v.i;
+    if (u.j != v.j) return u.j < v.j;
+    return u.k < v.k;
+  });
+  std::vector<int> me_ptr, me_i, me_j, mt_k;
+  std::vector<double> mt_w;
+  for (size_t t = 0; t < tr.size(); t++) {
+    if (t == 0 || tr[t].i != tr[t - 1].i || tr[t].j != tr[t - 1].j) {
+      me_ptr.push_back((int)t);
+      me_i.push_back(tr[t].i);
+      me_j.push_back(tr[t].j);
+    }
+    mt_k.push_back(tr[t].k);
+    mt_w.push_back(tr[t].w);
+  }
+  me_ptr.push_back((int)tr.size());
+  M.nme = (int)me_i.size();
+  int rc;
+  if ((rc = upload(e, Ap, &M.Ap))) return rc;
+  if ((rc = upload(e, Ai, &M.Ai))) return rc;
+  if ((rc = upload(e, Ax, &M.Ax))) return rc;
+  if ((rc = upload(e, Tp, &M.Tp))) return rc;
+  if ((rc = upload(e, Ti, &M.Ti))) return rc;
+  if ((rc = upload(e, Tx, &M.Tx))) return rc;
+  if ((rc = upload(e, me_ptr, &M.me_ptr))) return rc;
+  if ((rc = upload(e, me_i, &M.me_i))) return rc;
+  if ((rc = upload(e, me_j, &M.me_j))) return rc;
+  if ((rc = upload(e, mt_k, &M.mt_k))) return rc;
+  if ((rc = upload(e, mt_w, &M.mt_w))) return rc;
+  return finish_setup(e, max_problems);
+}
+
+int pycllp_b200_set_params(pycllp_b200_engine* e, const pycllp_b200_params* p) {
+  if (!e || !p) return fail(e, PYCLLP_B200_ERR_ARG, "set_params: null argument");
+  if (p->max_iter < 0 || p->max_refine < 0 || !(p->r > 0))
+    return fail(e, PYCLLP_B200_ERR_ARG, "set_params: invalid value");
+  e->p.eps = p->eps; e->p.delta = p->delta; e->p.r = p->r; e->p.ldl_delta = p->ldl_delta;
+  e->p.refine_tol = p->refine_tol; e->p.max_iter = p->max_iter; e->p.max_refine = p->max_refine;
+  return 0;
+}
+
+int pycllp_b200_get_params(const pycllp_b200_engine* e, pycllp_b200_params* p) {
+  if (!e || !p) return PYCLLP_B200_ERR_ARG;
+  p->eps = e->p.eps; p->delta = e->p.delta; p->r = e->p.r; p->ldl_delta = e->p.ldl_delta;
+  p->refine_tol = e->p.refine_tol; p->max_iter = e->p.max_iter; p->max_refine = e->p.max_refine;
+  return 0;
+}
+
+int pycllp_b200_solve_device(pycllp_b200_engine* e, int N, const double* d_b, const double* d_c,
+                             double* d_x, double* d_y, double* d_z, int* d_status, int* d_iters,
+                             void* stream) {
+  if (!e) return PYCLLP_B200_ERR_ARG;
+  if (!e->ready) return fail(e, PYCLLP_B200_ERR_STATE, "solve: call setup_dense/setup_sparse first");
+  if (N < 0 || !d_b || !d_c) return fail(e, PYCLLP_B200_ERR_ARG, "solve: bad argument");
+  if (N == 0) return 0;
+  DeviceGuard guard(e->device);
+  Batch B{};
+  B.N = N; B.b = d_b; B.c = d_c; B.x = d_x; B.y = d_y; B.z = d_z;
+  B.status = d_status; B.iters = d_iters;
+  return run(e, B, (cudaStream_t)stream);
+}
+
+int pycllp_b200_solve_host(pycllp_b200_engine* e, int N, const double* b, const double* c,
+                           double* x, double* y, double* z, int* status, int* iters) {
+  if (!e) return PYCLLP_B200_ERR_ARG;
+  if (!e->ready) return fail(e, PYCLLP_B200_ERR_STATE, "solve: call setup_dense/setup_sparse first");
+  if (N < 0 || N > e->max_problems || !b || !c)
+    return fail(e, PYCLLP_B200_ERR_ARG, "solve: bad argument (N > max_problems?)");
+  if (N == 0) return 0;
+  DeviceGuard guard(e->device);
+  const size_t m = e->A.m, n = e->A.n;
+  cudaStream_t s = e->stream;
+  CU(cudaMemcpyAsync(e->d_b, b, N * m * sizeof(double), cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(e->d_c, c, N * n * sizeof(double), cudaMemcpyHostToDevice, s));
+  Batch B{};
+  B.N = N; B.b = e->d_b; B.c = e->d_c; B.x = e->d_x; B.y = e->d_y; B.z = e->d_z;
+  B.status = e->d_status; B.iters = e->d_iters;
+  int rc = run(e, B, s);
+  if (rc) return rc;
+  if (x) CU(cudaMemcpyAsync(x, e->d_x, N * n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (y) CU(cudaMemcpyAsync(y, e->d_y, N * m * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (z) CU(cudaMemcpyAsync(z, e->d_z, N * n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (status) CU(cudaMemcpyAsync(status, e->d_status, N * sizeof(int), cudaMemcpyDeviceToHost, s));
+  if (iters) CU(cudaMemcpyAsync(iters, e->d_iters, N * sizeof(int), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int pycllp_b200_solve_primal_normal(pycllp_b200_engine* e, int N, const double* x,
+                                    const double* z, const double* y, const double* b,
+                                    const double* c, double mu, double* dy) {
+  if (!e) return PYCLLP_B200_ERR_ARG;
+  if (!e->ready) return fail(e, PYCLLP_B200_ERR_STATE, "solve_primal_normal: call setup first");
+  if (N <= 0 || N > e->max_problems || !x || !z || !y || !b || !c || !dy)
+    return fail(e, PYCLLP_B200_ERR_ARG, "solve_primal_normal: bad argument");
+  DeviceGuard guard(e->device);
+  const size_t m = e->A.m, n = e->A.n;
+  cudaStream_t s = e->stream;
+  // staging: d_b <- b, d_c <- c, d_x <- x, d_z <- z, d_y <- y ; dy comes back through d_status? no:
+  double* d_dy = nullptr;
+  CU(cudaMalloc(&d_dy, N * m * sizeof(double)));
+  cudaError_t err = cudaSuccess;
+  auto cp = [&](void* d, const void* h, size_t bytes) {
+    if (err == cudaSuccess) err = cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, s);
+  };
+  cp(e->d_b, b, N * m * sizeof(double));
+  cp(e->d_c, c, N * n * sizeof(double));
+  cp(e->d_x, x, N * n * sizeof(double));
+  cp(e->d_z, z, N * n * sizeof(double));
+  cp(e->d_y, y, N * m * sizeof(double));
+  int rc = 0;
+  if (err == cudaSuccess) {
+    Batch B{};
+    B.N = N; B.b = e->d_b; B.c = e->d_c; B.hook = 1;
+    B.x0 = e->d_x; B.z0 = e->d_z; B.y0 = e->d_y; B.dy_out = d_dy; B.mu = mu;
+    rc = run(e, B, s);
+    if (!rc) err = cudaMemcpyAsync(dy, d_dy, N * m * sizeof(double), cudaMemcpyDeviceToHost, s);
+    if (!rc && err == cudaSuccess) err = cudaStreamSynchronize(s);
+  }
+  cudaStreamSynchronize(s);
+  cudaFree(d_dy);
+  if (rc) return rc;
+  if (err != cudaSuccess) return fail(e, PYCLLP_B200_ERR_CUDA, cudaGetErrorString(err));
+  return 0;
+}
+
+int pycllp_b200_ldl(pycllp_b200_engine* e, int N, int m, const double* AA, double* L, double* D,
+                    int modified, double beta, double delta) {
+  if (!e) return PYCLLP_B200_ERR_ARG;
+  if (N <= 0 || m <= 0 || !AA || !L || !D) return fail(e, PYCLLP_B200_ERR_ARG, "ldl: bad argument");
+  DeviceGuard guard(e->device);
+  const size_t lsz = (size_t)m * (m + 1) / 2;
+  const size_t slot = al16((size_t)m * NB + lsz + m);
+  const int grid = std::min(N, e->num_sms);
+  double *d_AA = nullptr, *d_L = nullptr, *d_D = nullptr, *d_s = nullptr;
+  cudaError_t err = cudaMalloc(&d_AA, (size_t)N * m * m * sizeof(double));
+  if (err == cudaSuccess) err = cudaMalloc(&d_L, N * lsz * sizeof(double));
+  if (err == cudaSuccess) err = cudaMalloc(&d_D, (size_t)N * m * sizeof(double));
+  if (err == cudaSuccess) err = cudaMalloc(&d_s, slot * grid * sizeof(double));
+  cudaStream_t s = e->stream;
+  if (err == cudaSuccess)
+    err = cudaMemcpyAsync(d_AA, AA, (size_t)N * m * m * sizeof(double), cudaMemcpyHostToDevice, s);
+  if (err == cudaSuccess) {
+    err = launch_ldl_hook(N, m, d_AA, d_L, d_D, modified, beta, delta, d_s, slot, grid, s);
+    e->launches += 1;
+  }
+  if (err == cudaSuccess) err = cudaMemcpyAsync(L, d_L, N * lsz * sizeof(double), cudaMemcpyDeviceToHost, s);
+  if (err == cudaSuccess) err = cudaMemcpyAsync(D, d_D, (size_t)N * m * sizeof(double), cudaMemcpyDeviceToHost, s);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(s);
+  cudaStreamSynchronize(s);
+  cudaFree(d_AA); cudaFree(d_L); cudaFree(d_D); cudaFree(d_s);
+  if (err != cudaSuccess) return fail(e, PYCLLP_B200_ERR_CUDA, cudaGetErrorString(err));
+  return 0;
+}
+
+long long pycllp_b200_launch_count(const pycllp_b200_engine* e) { return e ? e->launches : 0; }
+
+int pycllp_b200_info(const pycllp_b200_engine* e, int* num_sms, int* grid, int* block,
+                     size_t* smem_bytes, size_t* scratch_bytes, int* factor_in_smem) {
+  if (!e) return PYCLLP_B200_ERR_ARG;
+  if (num_sms) *num_sms = e->num_sms;
+  if (grid) *grid = e->grid;
+  if (block) *block = NT;
+  if (smem_bytes) *smem_bytes = e->smem_bytes;
+  if (scratch_bytes) *scratch_bytes = e->sc.slot * sizeof(double) * (size_t)e->grid;
+  if (factor_in_smem) *factor_in_smem = e->sc.L_in_smem;
+  return 0;
+}
+
+}  // extern "C"

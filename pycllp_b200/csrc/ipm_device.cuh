@@ -1,0 +1,418 @@
+// ipm_device.cuh -- device side of the batched primal normal-equations IPM (sm_100a).
+//
+// One thread block solves one LP from start to finish (all <= 200 iterations),
+// then fetches the next LP from a global work counter: a persistent grid of
+// (#SMs x resident blocks) CTAs, no host round trips, no inter-block
+// synchronisation, and all per-problem state (x, z, y, the normal matrix M, its
+// LDL' factor) stays on-chip / in an L2-resident scratch slot owned by the block.
+//
+// What is computed follows the reference's OpenCL kernels exactly (same
+// constants, same stop rule, same modified LDL', same refinement rule):
+//   primal_normal.cl:201-284  standard_primal_normal          -> ipm_solve_one
+//   primal_normal.cl:30-120   primal/dual infeasibility       -> stage "residual norms"
+//   ldl.cl:110-138,280-294    A (X/Z) A' entries, beta        -> form_M_* (once/iteration)
+//   ldl.cl:314-378            factor_primal_normal            -> factor_ldl
+//   ldl.cl:198-219            primal_normal_rhs_i             -> RHS from the stored t
+//   ldl.cl:505-537            forward_backward_primal_normal  -> tri_solve
+//   ldl.cl:577-599            residual_primal_normal          -> residual_M
+//   ldl.cl:602-653            solve_primal_normal             -> solve_normal
+//   primal_normal.cl:122-156  primal_normal_step              -> step
+// How it is computed is different: M is formed ONCE per iteration (FP64 tensor-core
+// SYRK over the columns of A with >= 2 non-zeros, singleton/slack columns add to the
+// diagonal only), t = c - A'y + mu/x is evaluated ONCE and reused by the RHS and the
+// step, and all loops are block-cooperative.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include "ipm_types.h"
+
+namespace pb200 {
+
+// ---------------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// Deterministic block reductions; every thread gets the result. red: >= 32 doubles.
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_sum(v);
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  double r = (lane < NWARP) ? red[lane] : 0.0;
+  r = warp_sum(r);
+  __syncthreads();
+  return r;
+}
+__device__ __forceinline__ double block_max(double v, double* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_max(v);
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  double r = (lane < NWARP) ? red[lane] : 0.0;   // all callers reduce non-negative values
+  r = warp_max(r);
+  __syncthreads();
+  return r;
+}
+
+// packed lower triangle, COLUMN-major: column j holds rows j..m-1 contiguously, so that a
+// "thread per row" sweep over a column is a unit-stride access.
+__device__ __forceinline__ size_t cidx(int i, int j, int m) {
+  return (size_t)j * m - (size_t)j * (j - 1) / 2 + (i - j);
+}
+
+// D(8x8) += A(8x4) * B(4x8), FP64 tensor core (DMMA).
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// Per-block working set (pointers into shared memory or the block's scratch slot).
+struct Work {
+  double *x, *z, *c, *t, *d, *w;        // n each
+  double *y, *b, *dy, *S, *RHS, *D;     // m each
+  double* P;                            // max(m*NB, 2*TB*LDT): panel multipliers / SYRK tiles
+  double* dg;                           // ldd : d gathered on the packed SYRK columns
+  double* L;                            // m(m+1)/2 packed column-major
+  double* M;                            // m*m full symmetric (global scratch)
+  double* red;                          // 32 reduction scratch
+};
+
+// ---------------------------------------------------------------------------------------
+// operator A : v = A' u (n outputs)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void At_times(const Matrix& A, const double* __restrict__ u,
+                                         double* __restrict__ out) {
+  const int m = A.m, n = A.n;
+  if (!A.sparse) {
+    for (int j = threadIdx.x; j < n; j += NT) {
+      double acc = 0.0;
+      const double* __restrict__ col = A.A + j;
+#pragma unroll 4
+      for (int i = 0; i < m; i++) acc += col[(size_t)i * n] * u[i];
+      out[j] = acc;
+    }
+  } else {
+    for (int j = threadIdx.x; j < n; j += NT) {
+      double acc = 0.0;
+      for (int k = A.Tp[j]; k < A.Tp[j + 1]; k++) acc += A.Tx[k] * u[A.Ti[k]];
+      out[j] = acc;
+    }
+  }
+}
+
+// o1 = A u1, o2 = A u2 (m outputs each), one pass over A
+__device__ __forceinline__ void A_times2(const Matrix& A, const double* __restrict__ u1,
+                                         const double* __restrict__ u2, double* __restrict__ o1,
+                                         double* __restrict__ o2) {
+  const int m = A.m, n = A.n;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (!A.sparse) {
+    for (int i = warp; i < m; i += NWARP) {
+      const double* __restrict__ row = A.A + (size_t)i * n;
+      double a1 = 0.0, a2 = 0.0;
+      for (int j = lane; j < n; j += 32) {
+        double a = row[j];
+        a1 += a * u1[j];
+        a2 += a * u2[j];
+      }
+      a1 = warp_sum(a1);
+      a2 = warp_sum(a2);
+      if (lane == 0) { o1[i] = a1; o2[i] = a2; }
+    }
+  } else {
+    for (int i = warp; i < m; i += NWARP) {
+      double a1 = 0.0, a2 = 0.0;
+      for (int k = A.Ap[i] + lane; k < A.Ap[i + 1]; k += 32) {
+        double a = A.Ax[k];
+        int j = A.Ai[k];
+        a1 += a * u1[j];
+        a2 += a * u2[j];
+      }
+      a1 = warp_sum(a1);
+      a2 = warp_sum(a2);
+      if (lane == 0) { o1[i] = a1; o2[i] = a2; }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// M = A diag(d) A'  (full symmetric m x m into W.M), returns nothing; caller syncs.
+// ---------------------------------------------------------------------------------------
+static __device__ void form_M_dense(const Matrix& A, Work& W) {
+  const int m = A.m, ldd = A.ldd;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, tg = lane & 3;
+  const int wr = warp >> 2, wc = warp & 3;
+  double* As = W.P;
+  double* Bs = W.P + TB * LDT;
+  for (int k = tid; k < ldd; k += NT) W.dg[k] = (k < A.nd) ? W.d[A.dcols[k]] : 0.0;
+  const int nmt = (m + TB - 1) / TB;
+  for (int I = 0; I < nmt; I++) {
+    for (int J = 0; J <= I; J++) {
+      const bool active = !(I == J && wc > wr);
+      double acc[2][2][2];
+#pragma unroll
+      for (int a = 0; a < 2; a++)
+#pragma unroll
+        for (int b2 = 0; b2 < 2; b2++) acc[a][b2][0] = acc[a][b2][1] = 0.0;
+      for (int k0 = 0; k0 < ldd; k0 += KC) {
+        __syncthreads();   // previous chunk consumed (and dg written on the first pass)
+        for (int e = tid; e < TB * KC; e += NT) {
+          int r = e / KC, kk = e % KC;
+          int gi = I * TB + r, gj = J * TB + r;
+          As[r * LDT + kk] = (gi < m) ? A.Ad[(size_t)gi * ldd + k0 + kk] : 0.0;
+          Bs[r * LDT + kk] = (gj < m) ? A.Ad[(size_t)gj * ldd + k0 + kk] * W.dg[k0 + kk] : 0.0;
+        }
+        __syncthreads();
+        if (active) {
+#pragma unroll
+          for (int ks = 0; ks < KC / 4; ks++) {
+            double a0 = As[(wr * 16 + g) * LDT + ks * 4 + tg];
+            double a1 = As[(wr * 16 + 8 + g) * LDT + ks * 4 + tg];
+            double b0 = Bs[(wc * 16 + g) * LDT + ks * 4 + tg];
+            double b1 = Bs[(wc * 16 + 8 + g) * LDT + ks * 4 + tg];
+            dmma884(acc[0][0][0], acc[0][0][1], a0, b0);
+            dmma884(acc[0][1][0], acc[0][1][1], a0, b1);
+            dmma884(acc[1][0][0], acc[1][0][1], a1, b0);
+            dmma884(acc[1][1][0], acc[1][1][1], a1, b1);
+          }
+        }
+      }
+      if (active) {
+#pragma unroll
+        for (int ri = 0; ri < 2; ri++)
+#pragma unroll
+          for (int ci = 0; ci < 2; ci++)
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+              int i = I * TB + wr * 16 + ri * 8 + g;
+              int j = J * TB + wc * 16 + ci * 8 + tg * 2 + h;
+              if (i < m && j <= i) {
+                double v = acc[ri][ci][h];
+                W.M[(size_t)i * m + j] = v;
+                W.M[(size_t)j * m + i] = v;
+              }
+            }
+      }
+    }
+  }
+  __syncthreads();
+  // singleton (slack) columns: diagonal only
+  for (int i = tid; i < m; i += NT) {
+    double s = 0.0;
+    for (int e = A.sing_ptr[i]; e < A.sing_ptr[i + 1]; e++) s += A.sing_w[e] * W.d[A.sing_col[e]];
+    if (A.sing_ptr[i + 1] > A.sing_ptr[i]) W.M[(size_t)i * m + i] += s;
+  }
+}
+
+static __device__ void form_M_sparse(const Matrix& A, Work& W) {
+  const int m = A.m;
+  for (int e = threadIdx.x; e < A.nme; e += NT) {
+    double s = 0.0;
+    for (int t = A.me_ptr[e]; t < A.me_ptr[e + 1]; t++) s += A.mt_w[t] * W.d[A.mt_k[t]];
+    int i = A.me_i[e], j = A.me_j[e];
+    W.M[(size_t)i * m + j] = s;
+    W.M[(size_t)j * m + i] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// (modified) LDL' of W.M (lower part) -> W.L (unit lower, packed column-major), W.D
+//   ldl.cl:349-376 : Dj = M_jj - sum_k D_k L_jk^2 ; c_ij = M_ij - sum_k L_ik L_jk D_k ;
+//                    theta = max_i |c_ij| ; Dj = max(|Dj|, (theta/beta)^2, delta) ; L_ij = c_ij/Dj
+//   plain != 0     : ldl.cl:28-55 (no clamping).
+// Left-looking by panels of NB columns, one thread per row.
+// ---------------------------------------------------------------------------------------
+static __device__ void factor_ldl(int m, Work& W, double beta, double delta, int plain) {
+  const int tid = threadIdx.x;
+  double* __restrict__ L = W.L;
+  double* __restrict__ D = W.D;
+  double* __restrict__ P = W.P;
+  const double* __restrict__ M = W.M;
+  for (int j0 = 0; j0 < m; j0 += NB) {
+    const int nb = min(NB, m - j0);
+    // P[k][jj] = L(j0+jj, k) * D[k]
+    for (int e = tid; e < j0 * NB; e += NT) {
+      int k = e / NB, jj = e % NB;
+      P[e] = (jj < nb) ? L[cidx(j0 + jj, k, m)] * D[k] : 0.0;
+    }
+    __syncthreads();
+    for (int i = j0 + tid; i < m; i += NT) {
+      double acc[NB];
+#pragma unroll
+      for (int jj = 0; jj < NB; jj++) acc[jj] = (jj < nb) ? M[(size_t)i * m + j0 + jj] : 0.0;
+      for (int k = 0; k < j0; k++) {
+        double lik = L[cidx(i, k, m)];
+        const double* pk = P + k * NB;
+#pragma unroll
+        for (int jj = 0; jj < NB; jj++) acc[jj] -= lik * pk[jj];
+      }
+#pragma unroll
+      for (int jj = 0; jj < NB; jj++)
+        if (jj < nb && j0 + jj <= i) L[cidx(i, j0 + jj, m)] = acc[jj];
+    }
+    __syncthreads();
+    // eliminate inside the panel, one column at a time
+    for (int jj = 0; jj < nb; jj++) {
+      const int j = j0 + jj;
+      const double djraw = L[cidx(j, j, m)];
+      double Dj;
+      if (plain) {
+        Dj = djraw;
+        __syncthreads();   // everyone has read L(j,j)
+      } else {
+        double th = 0.0;
+        for (int i = j + 1 + tid; i < m; i += NT) th = fmax(th, fabs(L[cidx(i, j, m)]));
+        th = block_max(th, W.red);
+        double q = th / beta;
+        Dj = fmax(fabs(djraw), fmax(q * q, delta));
+      }
+      for (int i = j + 1 + tid; i < m; i += NT) L[cidx(i, j, m)] /= Dj;
+      if (tid == 0) { D[j] = Dj; L[cidx(j, j, m)] = 1.0; }
+      __syncthreads();
+      if (jj + 1 < nb) {
+        for (int i = j + 1 + tid; i < m; i += NT) {
+          double lij = L[cidx(i, j, m)];
+          for (int j2 = j + 1; j2 < j0 + nb && j2 <= i; j2++)
+            L[cidx(i, j2, m)] -= lij * (Dj * L[cidx(j2, j, m)]);
+        }
+        __syncthreads();
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// S <- (L D)^-1 S ; S <- L^-T S ; dy += S      (ldl.cl:519-536), warp 0 only.
+// ---------------------------------------------------------------------------------------
+static __device__ void tri_solve(int m, Work& W) {
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    double* __restrict__ S = W.S;
+    const double* __restrict__ L = W.L;
+    const double* __restrict__ D = W.D;
+    for (int j = 0; j < m; j++) {
+      double dj = D[j];
+      double sj = S[j] / dj;
+      const double* col = L + cidx(j, j, m) - j;   // col[i] = L(i, j)
+      for (int i = j + 1 + lane; i < m; i += 32) S[i] -= sj * col[i] * dj;
+      __syncwarp();
+      if (lane == 0) S[j] = sj;
+    }
+    __syncwarp();
+    for (int j = m - 1; j >= 0; j--) {
+      const double* col = L + cidx(j, j, m) - j;
+      double acc = 0.0;
+      for (int i = j + 1 + lane; i < m; i += 32) acc += S[i] * col[i];
+      acc = warp_sum(acc);
+      if (lane == 0) {
+        double sj = S[j] - acc;
+        S[j] = sj;
+        W.dy[j] += sj;
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+}
+
+// S = RHS - M dy ; returns max |S|   (ldl.cl:577-599)
+static __device__ double residual_M(int m, Work& W) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double mx = 0.0;
+  for (int i = warp; i < m; i += NWARP) {
+    const double* __restrict__ row = W.M + (size_t)i * m;
+    double acc = 0.0;
+    for (int j = lane; j < m; j += 32) acc += row[j] * W.dy[j];
+    acc = warp_sum(acc);
+    double r = W.RHS[i] - acc;
+    if (lane == 0) W.S[i] = r;
+    mx = fmax(mx, fabs(r));
+  }
+  return block_max(mx, W.red);
+}
+
+// factor + solve + refinement (ldl.cl:602-653); requires W.d, W.RHS set. Leaves dy.
+static __device__ void solve_normal(const Matrix& A, Work& W, const Params& p) {
+  const int m = A.m, tid = threadIdx.x;
+  if (A.sparse) form_M_sparse(A, W); else form_M_dense(A, W);
+  __syncthreads();
+  double bmax = 0.0;
+  for (int i = tid; i < m; i += NT) bmax = fmax(bmax, fabs(W.M[(size_t)i * m + i]));
+  const double beta = sqrt(block_max(bmax, W.red));
+  factor_ldl(m, W, beta, p.ldl_delta, 0);
+  for (int i = tid; i < m; i += NT) { W.dy[i] = 0.0; W.S[i] = W.RHS[i]; }
+  __syncthreads();
+  tri_solve(m, W);
+  double maxr = residual_M(m, W);
+  int nref = 0;
+  while (maxr > p.refine_tol && nref < p.max_refine) {
+    tri_solve(m, W);
+    maxr = residual_M(m, W);
+    nref++;
+  }
+}
+
+// Given x, z, y (and mu): v = A'y -> W.w ; t, d ; q -> W.w ; RHS ; also rho/sigma norms.
+// Returns through refs. After this W.t holds t = c - A'y + mu/x (the ONE evaluation).
+static __device__ void prepare_rhs(const Matrix& A, Work& W, double mu, double& normr, double& norms) {
+  const int m = A.m, n = A.n, tid = threadIdx.x;
+  At_times(A, W.y, W.w);                      // own outputs only: no sync needed before reuse
+  double ss = 0.0;
+  for (int j = tid; j < n; j += NT) {
+    double v = W.w[j], xj = W.x[j], zj = W.z[j], cj = W.c[j];
+    double sig = cj - v + zj;
+    ss += sig * sig;
+    double tj = cj - v + mu / xj;
+    W.t[j] = tj;
+    W.d[j] = xj / zj;
+    W.w[j] = xj * tj / zj;                     // q_j
+  }
+  norms = sqrt(block_sum(ss, W.red));          // (syncs: t, d, q visible)
+  // S <- A x ; RHS <- A q
+  A_times2(A, W.x, W.w, W.S, W.RHS);
+  __syncthreads();
+  double rr = 0.0;
+  for (int i = tid; i < m; i += NT) {
+    double rho = W.b[i] - W.S[i];
+    rr += rho * rho;
+    W.RHS[i] = W.RHS[i] - rho;                 // -(b - Ax - Aq)
+  }
+  normr = sqrt(block_sum(rr, W.red));
+}
+
+// dx, dz, ratio test, update (primal_normal.cl:122-156) using the stored t.
+static __device__ void step(const Matrix& A, Work& W, double mu, double r) {
+  const int m = A.m, n = A.n, tid = threadIdx.x;
+  At_times(A, W.dy, W.w);
+  double th = 0.0;
+  for (int j = tid; j < n; j += NT) {
+    double xj = W.x[j], zj = W.z[j];
+    double dx = (W.t[j] - W.w[j]) * xj / zj;
+    double dz = (mu - zj * dx) / xj - zj;
+    th = fmax(th, fmax(-dz / zj, -dx / xj));
+    W.w[j] = dx;
+    W.t[j] = dz;
+  }
+  th = block_max(th, W.red);
+  const double theta = fmin(r / th, 1.0);
+  for (int j = tid; j < n; j += NT) {
+    W.z[j] += theta * W.t[j];
+    W.x[j] += theta * W.w[j];
+  }
+  for (int i = tid; i < m; i += NT) W.y[i] += theta * W.dy[i];
+  __syncthreads();
+}
+
+}  // namespace pb200

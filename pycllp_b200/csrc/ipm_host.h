@@ -1,0 +1,17 @@
+// ipm_host.h -- host-callable launch helpers shared by ipm_kernels.cu and cabi.cu
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+#include "ipm_types.h"
+
+namespace pb200 {
+
+size_t smem_doubles(const Matrix& A, int L_in_smem, int vec_in_smem);
+cudaError_t launch_solve(const Matrix& A, const Batch& B, const Scratch& sc, const Params& p,
+                         int grid, size_t smem_bytes, cudaStream_t stream);
+cudaError_t launch_ldl_hook(int N, int m, const double* AA, double* L, double* D, int modified,
+                            double beta, double delta, double* scratch, size_t slot, int grid,
+                            cudaStream_t stream);
+int solve_kernel_max_blocks_per_sm(size_t smem_bytes);
+}  // namespace pb200

@@ -1,0 +1,164 @@
+// ipm_kernels.cu -- __global__ entry points of the batched IPM engine (sm_100a).
+#include "ipm_device.cuh"
+#include "ipm_host.h"
+
+namespace pb200 {
+
+__device__ __forceinline__ size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
+
+// Carve the block's working set out of shared memory / its scratch slot.
+static __device__ void carve(const Matrix& A, const Scratch& sc, double* smem, Work& W) {
+  const int m = A.m, n = A.n;
+  double* slot = sc.base + (size_t)blockIdx.x * sc.slot;
+  size_t o = 0;
+  W.red = smem + o; o += 32;
+  size_t psz = (size_t)m * NB;
+  if (psz < 2 * TB * LDT) psz = 2 * TB * LDT;
+  W.P = smem + o; o += align16(psz);
+  W.dg = smem + o; o += align16(A.ldd > 0 ? A.ldd : 1);
+  double* v = sc.vec_in_smem ? (smem + o) : (slot + sc.off_vec);
+  if (sc.vec_in_smem) o += align16((size_t)6 * n + 6 * m);
+  W.x = v; W.z = v + n; W.c = v + 2 * n; W.t = v + 3 * n; W.d = v + 4 * n; W.w = v + 5 * n;
+  double* u = v + 6 * (size_t)n;
+  W.y = u; W.b = u + m; W.dy = u + 2 * m; W.S = u + 3 * m; W.RHS = u + 4 * m; W.D = u + 5 * m;
+  W.L = sc.L_in_smem ? (smem + o) : (slot + sc.off_L);
+  W.M = slot;
+}
+
+static __device__ void ipm_solve_one(const Matrix& A, const Batch& B, Work& W, const Params& p, int q) {
+  const int m = A.m, n = A.n, tid = threadIdx.x;
+  for (int j = tid; j < n; j += NT) {
+    W.c[j] = B.c[(size_t)q * n + j];
+    W.x[j] = B.hook ? B.x0[(size_t)q * n + j] : 1.0;   // initialize_xzyw, primal_normal.cl:14-28
+    W.z[j] = B.hook ? B.z0[(size_t)q * n + j] : 1.0;
+  }
+  for (int i = tid; i < m; i += NT) {
+    W.b[i] = B.b[(size_t)q * m + i];
+    W.y[i] = B.hook ? B.y0[(size_t)q * m + i] : 1.0;
+  }
+  __syncthreads();
+
+  if (B.hook) {   // one solve_primal_normal (ldl.cl:602-653) on the given state
+    double nr, ns;
+    prepare_rhs(A, W, B.mu, nr, ns);
+    solve_normal(A, W, p);
+    for (int i = tid; i < m; i += NT) B.dy_out[(size_t)q * m + i] = W.dy[i];
+    __syncthreads();
+    return;
+  }
+
+  int stat = 5;                                   // primal_normal.cl:225
+  double normr0 = INFINITY, norms0 = INFINITY;    // HUGE_VALF/10, :227-228
+  int iter;
+  for (iter = 0; iter < p.max_iter; iter++) {
+    double g = 0.0;
+    for (int j = tid; j < n; j += NT) g += W.z[j] * W.x[j];
+    const double gamma = block_sum(g, W.red);
+    const double mu = p.delta * gamma / (double)(n + m);          // :272
+    double normr, norms;
+    prepare_rhs(A, W, mu, normr, norms);
+    if (normr < p.eps && norms < p.eps && gamma < p.eps) { stat = 0; break; }   // :256-259
+    if (normr > 10 * normr0 && normr > p.eps) { stat = 2; break; }              // :261-264
+    if (norms > 10 * norms0 && norms > p.eps) { stat = 4; break; }              // :266-269
+    solve_normal(A, W, p);
+    step(A, W, mu, p.r);
+    normr0 = normr;
+    norms0 = norms;
+  }
+  if (B.x) for (int j = tid; j < n; j += NT) B.x[(size_t)q * n + j] = W.x[j];
+  if (B.z) for (int j = tid; j < n; j += NT) B.z[(size_t)q * n + j] = W.z[j];
+  if (B.y) for (int i = tid; i < m; i += NT) B.y[(size_t)q * m + i] = W.y[i];
+  if (tid == 0) {
+    if (B.status) B.status[q] = stat;
+    if (B.iters) B.iters[q] = iter;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(NT, 1)
+ipm_solve_kernel(Matrix A, Batch B, Scratch sc, Params p) {
+  extern __shared__ __align__(16) double smem[];
+  __shared__ int s_next;
+  Work W;
+  carve(A, sc, smem, W);
+  if (A.sparse) {   // entries outside the pattern of A A' are never written again
+    const size_t mm = (size_t)A.m * A.m;
+    for (size_t e = threadIdx.x; e < mm; e += NT) W.M[e] = 0.0;
+    __syncthreads();
+  }
+  for (;;) {
+    if (threadIdx.x == 0) s_next = atomicAdd(sc.counter, 1);
+    __syncthreads();
+    const int q = s_next;
+    __syncthreads();
+    if (q >= B.N) break;
+    ipm_solve_one(A, B, W, p, q);
+  }
+}
+
+// (modified) LDL' of given dense matrices -- the reference's `ldl` / `modified_ldl`
+// kernels (ldl.cl:28-107), test hook.
+__global__ void __launch_bounds__(NT, 1)
+ldl_hook_kernel(int N, int m, const double* AA, double* Lout, double* Dout, int modified,
+                double beta, double delta, double* scratch, size_t slot) {
+  extern __shared__ __align__(16) double smem[];
+  Work W;
+  double* s = scratch + (size_t)blockIdx.x * slot;
+  const size_t lsz = (size_t)m * (m + 1) / 2;
+  W.red = smem;
+  W.P = s;
+  W.L = s + (size_t)m * NB;
+  W.D = W.L + lsz;
+  for (int q = blockIdx.x; q < N; q += gridDim.x) {
+    W.M = const_cast<double*>(AA) + (size_t)q * m * m;
+    factor_ldl(m, W, beta, delta, !modified);
+    __syncthreads();
+    for (int i = threadIdx.x; i < m; i += NT) {
+      Dout[(size_t)q * m + i] = W.D[i];
+      for (int j = 0; j <= i; j++)
+        Lout[q * lsz + (size_t)i * (i + 1) / 2 + j] = W.L[cidx(i, j, m)];
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// host-side launch helpers (called from cabi.cu)
+// ---------------------------------------------------------------------------------------
+size_t smem_doubles(const Matrix& A, int L_in_smem, int vec_in_smem) {
+  auto al = [](size_t v) { return (v + 15) & ~(size_t)15; };
+  size_t psz = (size_t)A.m * NB;
+  if (psz < 2 * TB * LDT) psz = 2 * TB * LDT;
+  size_t o = 32 + al(psz) + al(A.ldd > 0 ? A.ldd : 1);
+  if (vec_in_smem) o += al((size_t)6 * A.n + 6 * A.m);
+  if (L_in_smem) o += (size_t)A.m * (A.m + 1) / 2;
+  return o;
+}
+
+cudaError_t launch_solve(const Matrix& A, const Batch& B, const Scratch& sc, const Params& p,
+                         int grid, size_t smem_bytes, cudaStream_t stream) {
+  cudaError_t err = cudaFuncSetAttribute(ipm_solve_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem_bytes);
+  if (err != cudaSuccess) return err;
+  ipm_solve_kernel<<<grid, NT, smem_bytes, stream>>>(A, B, sc, p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_ldl_hook(int N, int m, const double* AA, double* L, double* D, int modified,
+                            double beta, double delta, double* scratch, size_t slot, int grid,
+                            cudaStream_t stream) {
+  ldl_hook_kernel<<<grid, NT, 32 * sizeof(double), stream>>>(N, m, AA, L, D, modified, beta,
+                                                              delta, scratch, slot);
+  return cudaGetLastError();
+}
+
+int solve_kernel_max_blocks_per_sm(size_t smem_bytes) {
+  int nb = 0;
+  cudaFuncSetAttribute(ipm_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)smem_bytes);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ipm_solve_kernel, NT, smem_bytes);
+  return nb;
+}
+
+}  // namespace pb200

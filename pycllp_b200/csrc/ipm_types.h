@@ -1,0 +1,65 @@
+// ipm_types.h -- plain structs and tile constants shared by host (cabi.cu) and device code.
+#pragma once
+#include <stddef.h>
+
+namespace pb200 {
+
+constexpr int NT = 512;          // threads per block
+constexpr int NWARP = NT / 32;   // 16 warps
+constexpr int NB = 8;            // LDL' panel width
+constexpr int TB = 64;           // SYRK macro tile (TB x TB outputs per pass)
+constexpr int KC = 16;           // SYRK k-chunk staged in shared memory
+constexpr int LDT = KC + 4;      // padded leading dimension of a staged tile (conflict-free)
+
+struct Params {
+  double eps, delta, r, ldl_delta, refine_tol;
+  int max_iter, max_refine;
+};
+
+// The shared constraint matrix and everything precomputed from it at setup.
+struct Matrix {
+  int m, n, sparse;
+  // dense operator (row-major m x n)
+  const double* A;
+  // SYRK operand: the nd columns of A with >= 2 non-zeros, packed m x ldd row-major
+  int nd, ldd;
+  const double* Ad;
+  const int* dcols;        // [ldd] original column of packed column k (padding -> 0)
+  // singleton columns (exactly one non-zero a in row i): M_ii += a^2 d_k ; CSR by row
+  const int* sing_ptr;     // [m+1]
+  const int* sing_col;     // original column index
+  const double* sing_w;    // a^2
+  // sparse operator: CSR of A and of A'
+  const int *Ap, *Ai;
+  const double* Ax;
+  const int *Tp, *Ti;
+  const double* Tx;
+  // sparse M formation: lower-triangle entries e=(i,j) of the pattern of A A' and the
+  // list of (k, w = A_ik A_jk) contributing to each
+  int nme;
+  const int *me_ptr, *me_i, *me_j, *mt_k;
+  const double* mt_w;
+};
+
+struct Batch {
+  int N;
+  const double *b, *c;     // (N, m), (N, n)
+  double *x, *y, *z;       // (N, n), (N, m), (N, n)   (may be null)
+  int *status, *iters;     // (N)                      (may be null)
+  // hook mode (one normal-equations solve on given state): x0,z0 (N,n), y0 (N,m) in, dy out
+  int hook;
+  const double *x0, *z0, *y0;
+  double* dy_out;
+  double mu;
+};
+
+struct Scratch {
+  double* base;       // per-block slots
+  size_t slot;        // doubles per slot
+  size_t off_L;       // offset of L inside the slot (if not in smem)
+  size_t off_vec;     // offset of the vectors inside the slot (if not in smem)
+  int* counter;       // work counter
+  int L_in_smem, vec_in_smem;
+};
+
+}  // namespace pb200

@@ -1,0 +1,235 @@
+"""Parity of the CUDA engine (through the C ABI) with the oracle / the reference's golden
+vectors.  The bar (BASELINE.json north_star): same termination status per problem,
+objective within 1e-8 relative, primal and dual solutions within 1e-6."""
+import numpy as np
+import pytest
+
+from conftest import golden, assert_parity, objective
+import problems
+
+pytestmark = pytest.mark.gpu
+
+DENSE_GOLDEN = ["cfg1_dense", "cfg2_vanderbei_2_9_dense", "cfg2_vanderbei_2_10_dense",
+                "cfg2_small_dense", "cfg3_sample", "cfg5_sample"]
+SPARSE_GOLDEN = ["cfg1_sparse", "cfg2_vanderbei_2_9_sparse", "cfg2_vanderbei_2_10_sparse",
+                 "cfg2_small_sparse", "cfg4_small_sparse"]
+
+
+def _dense(engine, A, b, c, **params):
+    engine.setup_dense(A, b.shape[0])
+    if params:
+        engine.set_params(**params)
+    return engine.solve_host(b, c)
+
+
+def _sparse(engine, A, b, c):
+    from scipy.sparse import csr_matrix
+    engine.setup_sparse(csr_matrix(A), b.shape[0])
+    return engine.solve_host(b, c)
+
+
+@pytest.mark.parametrize("name", DENSE_GOLDEN)
+def test_dense_vs_reference_golden(engine, name):
+    g = golden(name)
+    res = _dense(engine, g["A"], g["b"], g["c"])
+    assert_parity(res, g, g["c"], name)
+    assert np.abs(res["iters"] - g["iters"]).max() <= 1, "Newton step counts drifted"
+
+
+@pytest.mark.parametrize("name", SPARSE_GOLDEN)
+def test_sparse_vs_reference_golden(engine, name):
+    g = golden(name)
+    res = _sparse(engine, g["A"], g["b"], g["c"])
+    assert_parity(res, g, g["c"], name)
+    assert np.abs(res["iters"] - g["iters"]).max() <= 1
+
+
+def test_dense_vs_oracle_random_shapes(engine, oracle):
+    """Ragged shapes: m, n not multiples of the 8-wide tensor-core tiles / 64-wide macro tiles."""
+    rng = np.random.RandomState(5)
+    for m, n0, dens, N in [(1, 3, 1.0, 4), (7, 5, 1.0, 9), (13, 29, 0.5, 17), (65, 70, 0.3, 12),
+                           (130, 97, 1.0, 6)]:
+        A0 = rng.rand(m, n0) * (rng.rand(m, n0) < dens)
+        A = np.c_[A0, np.eye(m)]
+        b = 0.5 + rng.rand(N, m)
+        c = np.c_[0.5 + rng.rand(N, n0), np.zeros((N, m))]
+        ref = oracle.solve_dense(A, b, c)
+        assert_parity(_dense(engine, A, b, c), ref, c, "dense %dx%d" % (m, n0 + m))
+        refs = oracle.solve_sparse(A, b, c)
+        assert_parity(_sparse(engine, A, b, c), refs, c, "sparse %dx%d" % (m, n0 + m))
+
+
+def test_known_answers_through_the_plugin_api(engine):
+    """tests/test_vanderbei.py / test_simple.py through lp.init(solver) / lp.solve(solver)."""
+    from pycllp_b200.solvers import solver_registry
+    for fn in (problems.vanderbei_2_9, problems.vanderbei_2_10):
+        lp, xopt = fn()
+        elp = lp.to_equality_form() if isinstance(lp, problems.StandardLP) else lp
+        for name in ("cl_dense_primal_normal", "cl_sparse_primal_normal"):
+            solver = solver_registry[name]()
+            elp.init(solver)
+            assert elp.solve(solver) is None          # CL solvers return None (cl.py:85-124)
+            np.testing.assert_equal(solver.status, 0)
+            assert solver.x.shape == (1, elp.ncols) and solver.status.dtype == np.int32
+            np.testing.assert_allclose(solver.x[0, :len(xopt)], xopt, rtol=1e-6, atol=1e-6)
+    A, b, c, f = problems.small_problem()
+    lp = problems.StandardLP(A, b, c, f).to_equality_form()
+    solver = solver_registry["cl_dense_primal_normal"](None, None)   # (ctx, queue) positionals ignored
+    lp.init(solver, verbose=0)
+    lp.solve(solver, verbose=0)
+    np.testing.assert_equal(solver.status, 0)
+    np.testing.assert_allclose(solver.x[0, :3], (1.00997e-13, 1.22527e-12, 5.18790e+00), rtol=1e-1, atol=1e-1)
+
+
+def test_batched_perturbed_small_problem_vs_highs(engine):
+    """tests/test_simple.py:70-93 (32 perturbed problems), ground truth from HiGHS."""
+    from scipy.optimize import linprog
+    from pycllp_b200.solvers import solver_registry
+    A, b, c, f = problems.small_problem()
+    bb, cc = problems.perturb(b, c, 32)
+    lp = problems.StandardLP(A, bb, cc, f).to_equality_form()
+    for name in ("cl_dense_primal_normal", "cl_sparse_primal_normal"):
+        solver = solver_registry[name]()
+        lp.init(solver)
+        lp.solve(solver)
+        np.testing.assert_equal(solver.status, 0)
+        Ad = np.asarray(lp.A.todense())
+        for q in range(lp.nproblems):
+            h = linprog(-lp.c[q], A_eq=Ad, b_eq=lp.b[q], bounds=(0, None), method="highs")
+            np.testing.assert_allclose(solver.x[q] @ lp.c[q], -h.fun, rtol=1e-6)
+
+
+@pytest.mark.parametrize("size", [10, 20])
+def test_random_vs_highs(engine, size):
+    from scipy.optimize import linprog
+    lp = problems.helpers_random_problem(size, size, 1.0, 1)
+    A, b, c = problems.equality_arrays(lp)
+    res = _dense(engine, A, b, c)
+    assert res["status"][0] == 0
+    h = linprog(-c[0], A_eq=A, b_eq=b[0], bounds=(0, None), method="highs")
+    np.testing.assert_allclose(res["x"][0] @ c[0], -h.fun, rtol=1e-6)
+    np.testing.assert_allclose(res["x"][0, :size], h.x[:size], rtol=1e-3, atol=1e-3)
+
+
+def test_kernel_solve_primal_normal(engine):
+    """tests/test_ldl.py:219-273 at the reference's own tolerance (1e-5), plus numpy."""
+    g = golden("kernel_solve_primal_normal")
+    engine.setup_dense(g["A"], g["x"].shape[0])
+    dy = engine.solve_primal_normal(g["x"], g["z"], g["y"], g["b"], g["c"], float(g["mu"]))
+    np.testing.assert_allclose(dy, g["dy"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(dy, g["dy"], rtol=1e-8, atol=1e-10)
+    A = g["A"]
+    x, z, y, b, c = (g[k][0] for k in "xzybc")
+    rhs = b - A @ x - (A * x / z) @ (c - A.T @ y + 1.0 / x)
+    np.testing.assert_allclose(dy[0], np.linalg.solve((A * x / z) @ A.T, -rhs), rtol=1e-7, atol=1e-9)
+
+
+def test_kernel_sparse_solve_primal_normal(engine):
+    """tests/test_ldl.py:276-361."""
+    from scipy.sparse import csr_matrix
+    g = golden("kernel_sparse_solve_primal_normal")
+    engine.setup_sparse(csr_matrix(g["A"]), g["x"].shape[0])
+    dy = engine.solve_primal_normal(g["x"], g["z"], g["y"], g["b"], g["c"], float(g["mu"]))
+    np.testing.assert_allclose(dy, g["dy"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(dy, g["dy"], rtol=1e-7, atol=1e-9)
+
+
+def test_kernel_ldl(engine):
+    """tests/test_ldl.py:139-193: `ldl`, `modified_ldl` at rtol 1e-6."""
+    g = golden("kernel_ldl")
+    L, D = engine.ldl(g["AA"], modified=False)
+    np.testing.assert_allclose(D, g["D_plain"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(L, g["L_plain"], rtol=1e-6, atol=1e-7)
+    L, D = engine.ldl(g["AA"], modified=True, beta=float(g["beta"]), delta=1e-6)
+    np.testing.assert_allclose(D, g["D_mod"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(L, g["L_mod"], rtol=1e-6, atol=1e-7)
+
+
+def test_status_codes_and_params(engine, oracle):
+    """Non-optimal statuses agree with the oracle; max_iter gives status 5; empty batch ok."""
+    A = np.array([[1.0, 1.0, 1.0, 0.0], [1.0, 1.0, 0.0, 1.0]])
+    b = np.array([[-1.0, 2.0], [1.0, 2.0]])
+    c = np.array([[1.0, 1.0, 0.0, 0.0], [1.0, 1.0, 0.0, 0.0]])
+    ref = oracle.solve_dense(A, b, c)
+    res = _dense(engine, A, b, c)
+    np.testing.assert_array_equal(res["status"], ref.status)
+    assert res["status"][0] != 0
+    g = golden("cfg1_dense")
+    res = _dense(engine, g["A"], g["b"][:3], g["c"][:3], max_iter=3)
+    assert (res["status"] == 5).all() and (res["iters"] == 3).all()
+    p = engine.get_params()
+    assert p.max_iter == 3 and abs(p.eps - float(np.float32(1e-7))) < 1e-20
+    with pytest.raises(TypeError):
+        engine.set_params(nonsense=1)
+    with pytest.raises(ValueError):
+        engine.solve_host(g["b"][:3, :5], g["c"][:3])
+
+
+def test_errors_are_loud(engine):
+    from pycllp_b200._cabi import Engine
+    e2 = Engine(0)
+    with pytest.raises(RuntimeError, match="setup"):
+        e2._check(e2._lib.pycllp_b200_solve_host(e2._h, 1, None, None, None, None, None, None, None), "solve")
+    with pytest.raises(RuntimeError):
+        Engine(10 ** 6)
+    e2.close()
+
+
+def test_device_buffers_and_stream(engine):
+    """The device-pointer entry point used by the benchmark (torch only as the allocator)."""
+    import torch
+    g = golden("cfg1_dense")
+    N, m = g["b"].shape
+    n = g["c"].shape[1]
+    engine.setup_dense(g["A"], N)
+    dev = torch.device("cuda", 0)
+    b = torch.from_numpy(g["b"]).to(dev)
+    c = torch.from_numpy(g["c"]).to(dev)
+    x = torch.empty(N, n, dtype=torch.float64, device=dev)
+    y = torch.empty(N, m, dtype=torch.float64, device=dev)
+    z = torch.empty(N, n, dtype=torch.float64, device=dev)
+    st = torch.empty(N, dtype=torch.int32, device=dev)
+    it = torch.empty(N, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream(dev)
+    engine.solve_device(N, b.data_ptr(), c.data_ptr(), x.data_ptr(), y.data_ptr(), z.data_ptr(),
+                        st.data_ptr(), it.data_ptr(), stream.cuda_stream)
+    stream.synchronize()
+    res = dict(x=x.cpu().numpy(), y=y.cpu().numpy(), z=z.cpu().numpy(), status=st.cpu().numpy())
+    assert_parity(res, g, g["c"], "device buffers")
+
+
+def test_full_size_config3_properties(engine):
+    """Config 3 at full size (m=200, n=400, N=4096): checked through size-independent
+    properties -- every problem optimal, primal/dual residuals and the gap below the stop
+    tolerance, x, z >= 0, weak duality gap closed -- and exactly against the golden sample
+    (the first 8 problems of this very batch)."""
+    from pycllp_b200.problems import random_equality_arrays
+    A, b, c = random_equality_arrays(200, 200, 1.0, 4096)
+    g = golden("cfg3_sample")
+    if not np.array_equal(A, g["A"]):
+        A, b, c = g["A"], np.tile(g["b"], (512, 1)), np.tile(g["c"], (512, 1))
+    res = _dense(engine, A, b, c)
+    assert (res["status"] == 0).all()
+    x, y, z = res["x"], res["y"], res["z"]
+    eps = float(np.float32(1e-7))
+    assert np.linalg.norm(b - x @ A.T, axis=1).max() < eps
+    assert np.linalg.norm(c - y @ A + z, axis=1).max() < eps
+    assert np.einsum("ij,ij->i", x, z).max() < eps
+    assert x.min() > 0 and z.min() > 0
+    # primal objective c'x == dual objective b'y up to the gap (max c'x, A x = b; dual: A'y - z = c)
+    np.testing.assert_allclose(objective(x, c), np.einsum("ij,ij->i", y, b), rtol=1e-8)
+    sub = {k: v[:8] for k, v in res.items()}
+    assert_parity(sub, g, g["c"], "cfg3 head")
+    assert 20 <= res["iters"].min() and res["iters"].max() <= 40
+
+
+def test_repeat_solves_are_cold_starts_and_deterministic(engine):
+    """cl.py:108 re-initialises x = z = y = 1 on every solve; results are reproducible."""
+    g = golden("cfg1_dense")
+    engine.setup_dense(g["A"], 64)
+    r1 = engine.solve_host(g["b"], g["c"])
+    r2 = engine.solve_host(g["b"], g["c"])
+    for k in ("x", "y", "z", "status", "iters"):
+        assert np.array_equal(r1[k], r2[k])
+    r3 = engine.solve_host(g["b"][:5], g["c"][:5])      # N < max_problems
+    assert np.array_equal(r3["x"], r1["x"][:5])

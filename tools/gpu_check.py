@@ -1,0 +1,62 @@
+"""Ad-hoc GPU check: engine vs oracle on small configs + a first timing. Not a test."""
+import sys, time, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from pycllp_b200._cabi import Engine
+from pycllp_b200.problems import random_equality_arrays, sparse_equality_arrays
+from oracle.bindings import Oracle
+
+def compare(tag, res, ref):
+    st_ok = np.array_equal(res["status"], ref.status)
+    obj = lambda r, c: np.einsum("ij,ij->i", r["x"], c)
+    print(tag, "status equal:", st_ok, "iters diff max:", np.abs(res["iters"] - ref.iters).max(),
+          "| dx %.2e dy %.2e dz %.2e" % tuple(np.abs(res[k] - ref[k]).max() for k in "xyz"))
+    return st_ok
+
+o = Oracle()
+eng = Engine(0)
+which = sys.argv[1:] or ["cfg1", "cfg3s", "sparse", "time3"]
+if "cfg1" in which:
+    A, b, c = random_equality_arrays(50, 50, 0.1, 64)
+    eng.setup_dense(A, 64)
+    print(eng.info())
+    res = eng.solve_host(b, c)
+    ref = o.solve_dense(A, b, c)
+    compare("cfg1", res, ref)
+    print(" gpu iters", res["iters"][:16], "status", res["status"][:16])
+    rel = np.abs(np.einsum("ij,ij->i", res["x"], c) - np.einsum("ij,ij->i", ref.x, c)) / np.abs(np.einsum("ij,ij->i", ref.x, c))
+    print(" rel obj err max %.2e" % rel.max())
+if "cfg3s" in which:
+    A, b, c = random_equality_arrays(200, 200, 1.0, 16)
+    eng.setup_dense(A, 16)
+    print(eng.info())
+    res = eng.solve_host(b, c)
+    ref = o.solve_dense(A, b, c)
+    compare("cfg3 sample", res, ref)
+    print(" gpu iters", res["iters"], "oracle iters", ref.iters)
+if "sparse" in which:
+    A, b, c = sparse_equality_arrays(100, 150, 0.05, 16)
+    eng.setup_sparse(A, 16)
+    print(eng.info())
+    res = eng.solve_host(b, c)
+    ref = o.solve_sparse(A.toarray(), b, c)
+    compare("sparse", res, ref)
+    print(" gpu iters", res["iters"], "oracle iters", ref.iters)
+if "time3" in which:
+    N = 4096
+    A, b, c = random_equality_arrays(200, 200, 1.0, N)
+    eng.setup_dense(A, N)
+    print(eng.info())
+    for rep in range(3):
+        t = time.time(); res = eng.solve_host(b, c); dt = time.time() - t
+        print("cfg3 N=%d: %.3f s  -> %.0f solves/s; status hist %s; iters mean %.1f" % (
+            N, dt, N / dt, np.bincount(res["status"], minlength=6), res["iters"].mean()))
+if "time5" in which:
+    N = 592
+    A, b, c = random_equality_arrays(500, 500, 1.0, N)
+    eng.setup_dense(A, N)
+    print(eng.info())
+    for rep in range(2):
+        t = time.time(); res = eng.solve_host(b, c); dt = time.time() - t
+        print("cfg5 N=%d: %.3f s  -> %.0f solves/s; status hist %s; iters mean %.1f" % (
+            N, dt, N / dt, np.bincount(res["status"], minlength=6), res["iters"].mean()))
