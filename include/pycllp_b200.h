@@ -114,6 +114,13 @@ int pycllp_b200_solve_primal_normal(pycllp_b200_engine *e, int N, const double *
 int pycllp_b200_ldl(pycllp_b200_engine *e, int N, int m, const double *AA, double *L, double *D,
                     int modified, double beta, double delta);
 
+/* Profiling aid: per-phase SM cycle counters summed over blocks (thread 0 of each block,
+ * clock64). enable != 0 switches counting on (and zeroes the counters), 0 switches it off;
+ * out16 (may be NULL, 16 entries) receives the counters accumulated since the previous call:
+ * [0] rhs+norms [1] form M [2] factor [3] triangular solves [4] residual [5] step,
+ * [6..15] sub-phases of the factorisation / SYRK (see ipm_factor.cuh). */
+int pycllp_b200_phase_profile(pycllp_b200_engine *e, int enable, unsigned long long *out16);
+
 /* Introspection for the bench harness. */
 long long pycllp_b200_launch_count(const pycllp_b200_engine *e); /* kernels launched so far */
 int pycllp_b200_info(const pycllp_b200_engine *e, int *num_sms, int *grid, int *block,

@@ -124,7 +124,14 @@ void ref_sparse_solve_primal_normal(int N, int m, int n, double *Adata, int *Ain
 /* fired, or 199); trace[p*3..] = its (|rho|, |sigma|, gamma).                    */
 /* ------------------------------------------------------------------------- */
 
-#define REF_CHUNK 8
+#define REF_CHUNK_MAX 8
+/* problems per chunk: small enough that every host thread gets work */
+static int ref_chunk(int N, int nthreads) {
+  int c = (N + nthreads - 1) / nthreads;
+  if (c > REF_CHUNK_MAX) c = REF_CHUNK_MAX;
+  if (c < 1) c = 1;
+  return c;
+}
 
 typedef struct {
   int nnzL;
@@ -185,12 +192,13 @@ static void ref_run_chunk(int p0, int cn, int m, int n, const double *A, const r
 int ref_run_dense(int N, int m, int n, const double *A, const double *b, const double *c,
                   double *x, double *y, double *z, int *status, int *iters, double *trace,
                   int nthreads) {
-  int nchunks = (N + REF_CHUNK - 1) / REF_CHUNK;
   if (nthreads < 1) nthreads = 1;
+  const int CH = ref_chunk(N, nthreads);
+  int nchunks = (N + CH - 1) / CH;
 #pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
   for (int ch = 0; ch < nchunks; ch++) {
-    int p0 = ch * REF_CHUNK;
-    int cn = N - p0 < REF_CHUNK ? N - p0 : REF_CHUNK;
+    int p0 = ch * CH;
+    int cn = N - p0 < CH ? N - p0 : CH;
     ref_run_chunk(p0, cn, m, n, A, NULL, b, c, x, y, z, status, iters, trace);
   }
   return 0;
@@ -204,12 +212,13 @@ int ref_run_sparse(int N, int m, int n, const double *Adata, const int *Aindptr,
                    double *trace, int nthreads) {
   ref_sparse_t sp = {nnzL,  Lindptr, Lindices, LTindptr, LTindices, LTmap,
                      Adata, ATdata,  Aindptr,  Aindices, ATindptr,  ATindices};
-  int nchunks = (N + REF_CHUNK - 1) / REF_CHUNK;
   if (nthreads < 1) nthreads = 1;
+  const int CH = ref_chunk(N, nthreads);
+  int nchunks = (N + CH - 1) / CH;
 #pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
   for (int ch = 0; ch < nchunks; ch++) {
-    int p0 = ch * REF_CHUNK;
-    int cn = N - p0 < REF_CHUNK ? N - p0 : REF_CHUNK;
+    int p0 = ch * CH;
+    int cn = N - p0 < CH ? N - p0 : CH;
     ref_run_chunk(p0, cn, m, n, NULL, &sp, b, c, x, y, z, status, iters, trace);
   }
   return 0;

@@ -23,7 +23,7 @@ EXPORTS = (
     "pycllp_b200_setup_dense", "pycllp_b200_setup_sparse", "pycllp_b200_set_params",
     "pycllp_b200_get_params", "pycllp_b200_solve_host", "pycllp_b200_solve_device",
     "pycllp_b200_solve_primal_normal", "pycllp_b200_ldl", "pycllp_b200_launch_count",
-    "pycllp_b200_info",
+    "pycllp_b200_info", "pycllp_b200_phase_profile",
 )
 
 
@@ -66,6 +66,7 @@ def load_library():
     lib.pycllp_b200_launch_count.argtypes = [_vp]
     lib.pycllp_b200_info.argtypes = [_vp, _ip, _ip, _ip, ctypes.POINTER(ctypes.c_size_t),
                                      ctypes.POINTER(ctypes.c_size_t), _ip]
+    lib.pycllp_b200_phase_profile.argtypes = [_vp, ctypes.c_int, ctypes.POINTER(ctypes.c_ulonglong)]
     _lib = lib
     return lib
 
@@ -196,6 +197,14 @@ class Engine(object):
         self._check(self._lib.pycllp_b200_ldl(self._h, N, m, _d(AA), _d(L), _d(D), int(modified),
                                               float(beta), float(delta)), "pycllp_b200_ldl")
         return L, D
+
+    def phase_profile(self, enable=True):
+        """Per-phase SM cycles since the last call (dict), then (re)arm or disarm the counters."""
+        out = (ctypes.c_ulonglong * 16)()
+        self._check(self._lib.pycllp_b200_phase_profile(self._h, int(enable), out), "phase_profile")
+        names = ("rhs_norms", "form_M", "factor", "tri_solve", "residual", "step",
+                 "f_copy", "f_P", "f_stepA", "f_stepB", "f_stepC", "f_stepD", "s12", "s13", "s14", "s15")
+        return {k: int(out[i]) for i, k in enumerate(names)}
 
     # -- introspection ---------------------------------------------------------------------
     @property

@@ -30,6 +30,7 @@ struct pycllp_b200_engine {
   int *d_status = nullptr, *d_iters = nullptr;
   cudaStream_t stream = nullptr;
   long long launches = 0;
+  unsigned long long* d_prof = nullptr;   // phase counters (debug/profiling aid)
 };
 
 namespace {
@@ -89,6 +90,8 @@ void free_matrix(pycllp_b200_engine* e) {
     if (p) cudaFree(p);
   e->d_b = e->d_c = e->d_x = e->d_y = e->d_z = nullptr;
   e->d_status = e->d_iters = nullptr;
+  e->d_prof = nullptr;
+  e->sc.prof = nullptr;
   e->ready = false;
 }
 
@@ -237,7 +240,40 @@ int pycllp_b200_setup_dense(pycllp_b200_engine* e, int m, int n, const double* A
     sptr[i + 1] = (int)scol.size();
   }
   std::vector<double> Ah(A, A + (size_t)m * n);
+  // TMA-staged SYRK operand: chunks of SY_KC packed columns, k-major, rows padded to ldm
+  // with ldm = 4 (mod 16) so that the four k-rows of a DMMA fragment hit disjoint banks
+  int ldm = (m + 7) / 8 * 8;
+  while (ldm % 16 != 4) ldm++;
+  M.sy_ldm = ldm;
+  std::vector<double> Apk((size_t)M.ldd * ldm, 0.0);
+  for (int k = 0; k < M.nd; k++)
+    for (int i = 0; i < m; i++) Apk[(size_t)k * ldm + i] = A[(size_t)i * n + dcols[k]];
+  // tile segments: tile row I holds tiles J = 0..I, cut into runs of SY_CW; longest first,
+  // each to the least-loaded (pass, warp) that still has a free slot
+  {
+    const int T = (m + 7) / 8;
+    std::vector<int4> segs;
+    for (int I = 0; I < T; I++)
+      for (int J = 0; J <= I; J += SY_CW) segs.push_back(make_int4(I, J, std::min(SY_CW, I + 1 - J), 0));
+    std::stable_sort(segs.begin(), segs.end(), [](const int4& a, const int4& b) { return a.z > b.z; });
+    const int slots = NWARP * SY_SEG;
+    const int npass = std::max(1, ((int)segs.size() + slots - 1) / slots);
+    std::vector<int4> tab((size_t)npass * slots, make_int4(0, 0, 0, 0));
+    std::vector<int> load(npass * NWARP, 0), used(npass * NWARP, 0);
+    for (const int4& sg : segs) {
+      int best = -1;
+      for (int pw = 0; pw < npass * NWARP; pw++)
+        if (used[pw] < SY_SEG && (best < 0 || load[pw] < load[best])) best = pw;
+      tab[(size_t)best * SY_SEG + used[best]] = sg;
+      used[best]++;
+      load[best] += sg.z;
+    }
+    M.sy_npass = npass;
+    int rc2;
+    if ((rc2 = upload(e, tab, &M.sy_seg))) return rc2;
+  }
   int rc;
+  if ((rc = upload(e, Apk, &M.sy_A))) return rc;
   if ((rc = upload(e, Ah, &M.A))) return rc;
   if ((rc = upload(e, Ad, &M.Ad))) return rc;
   if ((rc = upload(e, dcols, &M.dcols))) return rc;
@@ -437,6 +473,30 @@ int pycllp_b200_ldl(pycllp_b200_engine* e, int N, int m, const double* AA, doubl
   cudaStreamSynchronize(s);
   cudaFree(d_AA); cudaFree(d_L); cudaFree(d_D); cudaFree(d_s);
   if (err != cudaSuccess) return fail(e, PYCLLP_B200_ERR_CUDA, cudaGetErrorString(err));
+  return 0;
+}
+
+int pycllp_b200_phase_profile(pycllp_b200_engine* e, int enable, unsigned long long* out16) {
+  if (!e) return PYCLLP_B200_ERR_ARG;
+  if (!e->ready) return fail(e, PYCLLP_B200_ERR_STATE, "phase_profile: call setup first");
+  DeviceGuard guard(e->device);
+  const size_t bytes = (size_t)e->grid * 16 * sizeof(unsigned long long);
+  if (out16) {
+    for (int k = 0; k < 16; k++) out16[k] = 0;
+    if (e->d_prof) {
+      std::vector<unsigned long long> h((size_t)e->grid * 16);
+      CU(cudaDeviceSynchronize());
+      CU(cudaMemcpy(h.data(), e->d_prof, bytes, cudaMemcpyDeviceToHost));
+      for (int g = 0; g < e->grid; g++)
+        for (int k = 0; k < 16; k++) out16[k] += h[(size_t)g * 16 + k];
+    }
+  }
+  if (enable && !e->d_prof) {
+    CU(cudaMalloc(&e->d_prof, bytes));
+    e->matrix_allocs.push_back(e->d_prof);
+  }
+  if (e->d_prof) CU(cudaMemset(e->d_prof, 0, bytes));
+  e->sc.prof = enable ? e->d_prof : nullptr;
   return 0;
 }
 

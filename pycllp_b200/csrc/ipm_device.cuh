@@ -85,8 +85,21 @@ struct Work {
   double* dg;                           // ldd : d gathered on the packed SYRK columns
   double* L;                            // m(m+1)/2 packed column-major
   double* M;                            // m*m full symmetric (global scratch)
-  double* red;                          // 32 reduction scratch
+  double* red;                          // 256: reductions [0,32) + panel scratch (ipm_factor.cuh)
+  unsigned long long* prof;             // per-phase cycle counters of this block (or null)
 };
+
+// phase ids: 0 rhs/norms, 1 form M, 2 factor, 3 triangular solves, 4 residual, 5 step
+// Counters accumulate in shared memory (W.red[224..240)) and are flushed once per kernel,
+// so that reading the clock does not put a global round trip on the critical path.
+constexpr int RED_PROF = 224;
+__device__ __forceinline__ long long phase_begin(const Work& W) {
+  return (W.prof && threadIdx.x == 0) ? clock64() : 0;
+}
+__device__ __forceinline__ void phase_end(const Work& W, int id, long long t0) {
+  if (W.prof && threadIdx.x == 0)
+    reinterpret_cast<unsigned long long*>(W.red + RED_PROF)[id] += (unsigned long long)(clock64() - t0);
+}
 
 // ---------------------------------------------------------------------------------------
 // operator A : v = A' u (n outputs)
@@ -293,8 +306,13 @@ static __device__ void factor_ldl(int m, Work& W, double beta, double delta, int
   }
 }
 
+}  // namespace pb200
+#include "ipm_factor.cuh"
+#include "ipm_syrk.cuh"
+namespace pb200 {
+
 // ---------------------------------------------------------------------------------------
-// S <- (L D)^-1 S ; S <- L^-T S ; dy += S      (ldl.cl:519-536), warp 0 only.
+// S <- (L D)^-1 S ; S <- L^-T S ; dy += S      (ldl.cl:519-536), warp 0 only (v1, unused).
 // ---------------------------------------------------------------------------------------
 static __device__ void tri_solve(int m, Work& W) {
   if (threadIdx.x < 32) {
@@ -346,20 +364,41 @@ static __device__ double residual_M(int m, Work& W) {
 // factor + solve + refinement (ldl.cl:602-653); requires W.d, W.RHS set. Leaves dy.
 static __device__ void solve_normal(const Matrix& A, Work& W, const Params& p) {
   const int m = A.m, tid = threadIdx.x;
-  if (A.sparse) form_M_sparse(A, W); else form_M_dense(A, W);
+  long long t0 = phase_begin(W);
+  if (A.sparse) form_M_sparse(A, W); else form_M_dense_tma(A, W);
   __syncthreads();
+  phase_end(W, 1, t0);
+  t0 = phase_begin(W);
   double bmax = 0.0;
   for (int i = tid; i < m; i += NT) bmax = fmax(bmax, fabs(W.M[(size_t)i * m + i]));
   const double beta = sqrt(block_max(bmax, W.red));
-  factor_ldl(m, W, beta, p.ldl_delta, 0);
-  for (int i = tid; i < m; i += NT) { W.dy[i] = 0.0; W.S[i] = W.RHS[i]; }
+  // the factorisation works in place on the packed lower triangle (the dense SYRK wrote it)
+  if (A.sparse) {
+    for (int e = tid; e < m * m; e += NT) {
+      const int j = e / m, i = e - j * m;
+      if (i >= j) W.L[cidx(i, j, m)] = W.M[(size_t)j * m + i];
+    }
+  }
+  for (int i = tid; i < m; i += NT) W.dy[i] = 0.0;
   __syncthreads();
-  tri_solve(m, W);
+  phase_end(W, 6, t0);
+  factor_ldl_fast(m, W, beta, p.ldl_delta, W.RHS, W.S);   // also S <- (L D)^-1 RHS
+  phase_end(W, 2, t0);
+  t0 = phase_begin(W);
+  back_solve_fast(m, W);
+  phase_end(W, 3, t0);
+  t0 = phase_begin(W);
   double maxr = residual_M(m, W);
+  phase_end(W, 4, t0);
   int nref = 0;
   while (maxr > p.refine_tol && nref < p.max_refine) {
-    tri_solve(m, W);
+    t0 = phase_begin(W);
+    fwd_solve_fast(m, W);
+    back_solve_fast(m, W);
+    phase_end(W, 3, t0);
+    t0 = phase_begin(W);
     maxr = residual_M(m, W);
+    phase_end(W, 4, t0);
     nref++;
   }
 }

@@ -11,9 +11,9 @@ static __device__ void carve(const Matrix& A, const Scratch& sc, double* smem, W
   const int m = A.m, n = A.n;
   double* slot = sc.base + (size_t)blockIdx.x * sc.slot;
   size_t o = 0;
-  W.red = smem + o; o += 32;
+  W.red = smem + o; o += RED_SIZE;
   size_t psz = (size_t)m * NB;
-  if (psz < 2 * TB * LDT) psz = 2 * TB * LDT;
+  if (psz < (size_t)2 * SY_KC * A.sy_ldm) psz = (size_t)2 * SY_KC * A.sy_ldm;
   W.P = smem + o; o += align16(psz);
   W.dg = smem + o; o += align16(A.ldd > 0 ? A.ldd : 1);
   double* v = sc.vec_in_smem ? (smem + o) : (slot + sc.off_vec);
@@ -23,6 +23,7 @@ static __device__ void carve(const Matrix& A, const Scratch& sc, double* smem, W
   W.y = u; W.b = u + m; W.dy = u + 2 * m; W.S = u + 3 * m; W.RHS = u + 4 * m; W.D = u + 5 * m;
   W.L = sc.L_in_smem ? (smem + o) : (slot + sc.off_L);
   W.M = slot;
+  W.prof = sc.prof ? sc.prof + (size_t)blockIdx.x * 16 : nullptr;
 }
 
 static __device__ void ipm_solve_one(const Matrix& A, const Batch& B, Work& W, const Params& p, int q) {
@@ -56,12 +57,16 @@ static __device__ void ipm_solve_one(const Matrix& A, const Batch& B, Work& W, c
     const double gamma = block_sum(g, W.red);
     const double mu = p.delta * gamma / (double)(n + m);          // :272
     double normr, norms;
+    long long t0 = phase_begin(W);
     prepare_rhs(A, W, mu, normr, norms);
+    phase_end(W, 0, t0);
     if (normr < p.eps && norms < p.eps && gamma < p.eps) { stat = 0; break; }   // :256-259
     if (normr > 10 * normr0 && normr > p.eps) { stat = 2; break; }              // :261-264
     if (norms > 10 * norms0 && norms > p.eps) { stat = 4; break; }              // :266-269
     solve_normal(A, W, p);
+    t0 = phase_begin(W);
     step(A, W, mu, p.r);
+    phase_end(W, 5, t0);
     normr0 = normr;
     norms0 = norms;
   }
@@ -81,6 +86,7 @@ ipm_solve_kernel(Matrix A, Batch B, Scratch sc, Params p) {
   __shared__ int s_next;
   Work W;
   carve(A, sc, smem, W);
+  if (W.prof && threadIdx.x < 16) reinterpret_cast<unsigned long long*>(W.red + RED_PROF)[threadIdx.x] = 0;
   if (A.sparse) {   // entries outside the pattern of A A' are never written again
     const size_t mm = (size_t)A.m * A.m;
     for (size_t e = threadIdx.x; e < mm; e += NT) W.M[e] = 0.0;
@@ -94,6 +100,8 @@ ipm_solve_kernel(Matrix A, Batch B, Scratch sc, Params p) {
     if (q >= B.N) break;
     ipm_solve_one(A, B, W, p, q);
   }
+  if (W.prof && threadIdx.x < 16)
+    W.prof[threadIdx.x] += reinterpret_cast<unsigned long long*>(W.red + RED_PROF)[threadIdx.x];
 }
 
 // (modified) LDL' of given dense matrices -- the reference's `ldl` / `modified_ldl`
@@ -109,9 +117,19 @@ ldl_hook_kernel(int N, int m, const double* AA, double* Lout, double* Dout, int 
   W.P = s;
   W.L = s + (size_t)m * NB;
   W.D = W.L + lsz;
+  W.prof = nullptr;
   for (int q = blockIdx.x; q < N; q += gridDim.x) {
     W.M = const_cast<double*>(AA) + (size_t)q * m * m;
-    factor_ldl(m, W, beta, delta, !modified);
+    if (modified) {
+      for (int e = threadIdx.x; e < m * m; e += NT) {
+        const int j = e / m, i = e - j * m;
+        if (i >= j) W.L[cidx(i, j, m)] = W.M[(size_t)j * m + i];
+      }
+      __syncthreads();
+      factor_ldl_fast(m, W, beta, delta, nullptr, nullptr);
+    } else {
+      factor_ldl(m, W, beta, delta, 1);
+    }
     __syncthreads();
     for (int i = threadIdx.x; i < m; i += NT) {
       Dout[(size_t)q * m + i] = W.D[i];
@@ -128,8 +146,8 @@ ldl_hook_kernel(int N, int m, const double* AA, double* Lout, double* Dout, int 
 size_t smem_doubles(const Matrix& A, int L_in_smem, int vec_in_smem) {
   auto al = [](size_t v) { return (v + 15) & ~(size_t)15; };
   size_t psz = (size_t)A.m * NB;
-  if (psz < 2 * TB * LDT) psz = 2 * TB * LDT;
-  size_t o = 32 + al(psz) + al(A.ldd > 0 ? A.ldd : 1);
+  if (psz < (size_t)2 * SY_KC * A.sy_ldm) psz = (size_t)2 * SY_KC * A.sy_ldm;
+  size_t o = RED_SIZE + al(psz) + al(A.ldd > 0 ? A.ldd : 1);
   if (vec_in_smem) o += al((size_t)6 * A.n + 6 * A.m);
   if (L_in_smem) o += (size_t)A.m * (A.m + 1) / 2;
   return o;
@@ -148,7 +166,7 @@ cudaError_t launch_solve(const Matrix& A, const Batch& B, const Scratch& sc, con
 cudaError_t launch_ldl_hook(int N, int m, const double* AA, double* L, double* D, int modified,
                             double beta, double delta, double* scratch, size_t slot, int grid,
                             cudaStream_t stream) {
-  ldl_hook_kernel<<<grid, NT, 32 * sizeof(double), stream>>>(N, m, AA, L, D, modified, beta,
+  ldl_hook_kernel<<<grid, NT, RED_SIZE * sizeof(double), stream>>>(N, m, AA, L, D, modified, beta,
                                                               delta, scratch, slot);
   return cudaGetLastError();
 }

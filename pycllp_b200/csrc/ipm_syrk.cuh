@@ -1,0 +1,152 @@
+// ipm_syrk.cuh -- M = A diag(d) A' on the FP64 tensor cores, operand staged by TMA.
+//
+// Only the nd columns of A with >= 2 non-zeros take part (singleton/slack columns add to the
+// diagonal afterwards).  The packed operand lives in global memory pre-tiled exactly as it
+// is used: chunk ch = SY_KC consecutive packed columns, stored k-major with the m rows padded
+// to SY ldm (ldm = 4 mod 16 makes every DMMA fragment load bank-conflict free), so one
+// cp.async.bulk (TMA, 1-D) brings a whole chunk into shared memory; two stages, one
+// mbarrier each.  The lower triangle of M is cut into 8x8 tiles; a warp owns up to SY_SEG
+// "segments" per pass (one tile row x up to SY_CW consecutive tile columns) and keeps their
+// accumulators in registers for the whole K loop, so every A fragment is loaded once per
+// SY_CW DMMAs and the row fragment is the one scaled by d (one DMUL per segment).  The
+// result goes straight into the factorisation's packed storage W.L and (both triangles)
+// into W.M for the residual.
+#pragma once
+
+namespace pb200 {
+
+constexpr int RED_MBAR = 216;   // two 8-byte mbarriers inside W.red
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+// 1-D bulk copy global -> shared, completion counted on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+static __device__ void form_M_dense_tma(const Matrix& A, Work& W) {
+  const int m = A.m, ldm = A.sy_ldm;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, tg = lane & 3;
+  const int nch = A.ldd / SY_KC;
+  const uint32_t chunk_bytes = (uint32_t)(SY_KC * ldm * sizeof(double));
+  double* stage0 = W.P;
+  double* stage1 = W.P + SY_KC * ldm;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(W.red + RED_MBAR);
+
+  for (int k = tid; k < A.ldd; k += NT) W.dg[k] = (k < A.nd) ? W.d[A.dcols[k]] : 0.0;
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  uint32_t ph0 = 0, ph1 = 0;   // phase parity of the two stage barriers
+
+  for (int pass = 0; pass < A.sy_npass; pass++) {
+    // this warp's segments: (tile row, first tile col, count)
+    int segI[SY_SEG], segJ[SY_SEG], segN[SY_SEG];
+#pragma unroll
+    for (int s = 0; s < SY_SEG; s++) {
+      const int4 e = A.sy_seg[(pass * NWARP + warp) * SY_SEG + s];
+      segI[s] = e.x; segJ[s] = e.y; segN[s] = e.z;
+    }
+    double acc[SY_SEG][SY_CW][2];
+#pragma unroll
+    for (int s = 0; s < SY_SEG; s++)
+#pragma unroll
+      for (int t = 0; t < SY_CW; t++) acc[s][t][0] = acc[s][t][1] = 0.0;
+
+    if (tid == 0) {
+      // the staging area was last touched through the generic proxy (factor's P / previous pass)
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(&bars[0], chunk_bytes);
+      tma_load_1d(stage0, A.sy_A, chunk_bytes, &bars[0]);
+    }
+    for (int ch = 0; ch < nch; ch++) {
+      const int st = ch & 1;
+      if (tid == 0 && ch + 1 < nch) {
+        uint64_t* nb = &bars[st ^ 1];
+        mbar_expect_tx(nb, chunk_bytes);
+        tma_load_1d(st ? stage0 : stage1, A.sy_A + (size_t)(ch + 1) * SY_KC * ldm, chunk_bytes, nb);
+      }
+      if (st == 0) { mbar_wait(&bars[0], ph0); ph0 ^= 1; }
+      else         { mbar_wait(&bars[1], ph1); ph1 ^= 1; }
+      const double* __restrict__ S = st ? stage1 : stage0;
+#pragma unroll
+      for (int ks = 0; ks < SY_KC / 4; ks++) {
+        const double dk = W.dg[ch * SY_KC + ks * 4 + tg];
+        const double* __restrict__ col = S + (ks * 4 + tg) * ldm + g;
+#pragma unroll
+        for (int s = 0; s < SY_SEG; s++) {
+          if (segN[s] > 0) {
+            const double as = col[8 * segI[s]] * dk;
+#pragma unroll
+            for (int t = 0; t < SY_CW; t++) {
+              if (t < segN[s]) {
+                const double b = col[8 * (segJ[s] + t)];
+                dmma884(acc[s][t][0], acc[s][t][1], as, b);
+              }
+            }
+          }
+        }
+      }
+      __syncthreads();   // every warp is done with stage st: it may be refilled
+    }
+    // epilogue: tiles -> packed L storage and full M
+#pragma unroll
+    for (int s = 0; s < SY_SEG; s++) {
+#pragma unroll
+      for (int t = 0; t < SY_CW; t++) {
+        if (t < segN[s]) {
+          const int i = 8 * segI[s] + g;
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            const int j = 8 * (segJ[s] + t) + 2 * tg + h;
+            if (i < m && j <= i) {
+              const double v = acc[s][t][h];
+              W.L[coff(j, m) + i] = v;
+              W.M[(size_t)i * m + j] = v;
+              W.M[(size_t)j * m + i] = v;
+            }
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // singleton (slack) columns: diagonal only
+  for (int i = tid; i < m; i += NT) {
+    if (A.sing_ptr[i + 1] > A.sing_ptr[i]) {
+      double s = 0.0;
+      for (int e = A.sing_ptr[i]; e < A.sing_ptr[i + 1]; e++) s += A.sing_w[e] * W.d[A.sing_col[e]];
+      const double v = W.M[(size_t)i * m + i] + s;
+      W.M[(size_t)i * m + i] = v;
+      W.L[coff(i, m) + i] = v;
+    }
+  }
+}
+
+}  // namespace pb200

@@ -1,6 +1,7 @@
 // ipm_types.h -- plain structs and tile constants shared by host (cabi.cu) and device code.
 #pragma once
 #include <stddef.h>
+#include <vector_types.h>
 
 namespace pb200 {
 
@@ -10,6 +11,9 @@ constexpr int NB = 8;            // LDL' panel width
 constexpr int TB = 64;           // SYRK macro tile (TB x TB outputs per pass)
 constexpr int KC = 16;           // SYRK k-chunk staged in shared memory
 constexpr int LDT = KC + 4;      // padded leading dimension of a staged tile (conflict-free)
+constexpr int SY_KC = 8;         // TMA-staged SYRK: packed columns per chunk
+constexpr int SY_SEG = 3;        //   segments per warp per pass
+constexpr int SY_CW = 4;         //   8x8 tiles per segment
 
 struct Params {
   double eps, delta, r, ldl_delta, refine_tol;
@@ -25,6 +29,11 @@ struct Matrix {
   int nd, ldd;
   const double* Ad;
   const int* dcols;        // [ldd] original column of packed column k (padding -> 0)
+  // TMA-staged SYRK (ipm_syrk.cuh): operand pre-tiled in chunks of SY_KC columns, k-major,
+  // rows padded to sy_ldm; per-(pass, warp, slot) tile segments {tile row, first tile col, count}
+  const double* sy_A;
+  int sy_ldm, sy_npass;
+  const int4* sy_seg;
   // singleton columns (exactly one non-zero a in row i): M_ii += a^2 d_k ; CSR by row
   const int* sing_ptr;     // [m+1]
   const int* sing_col;     // original column index
@@ -60,6 +69,7 @@ struct Scratch {
   size_t off_vec;     // offset of the vectors inside the slot (if not in smem)
   int* counter;       // work counter
   int L_in_smem, vec_in_smem;
+  unsigned long long* prof;   // optional [grid][8] per-phase cycle counters (null = off)
 };
 
 }  // namespace pb200

@@ -145,6 +145,22 @@ def test_kernel_ldl(engine):
     np.testing.assert_allclose(L, g["L_mod"], rtol=1e-6, atol=1e-7)
 
 
+def test_modified_ldl_with_active_theta_clamp(engine, oracle):
+    """A small beta makes (theta/beta)^2 exceed |D_j|: the engine's speculative panel
+    elimination must detect it and fall back to the sequential rule (ldl.cl:368)."""
+    g = golden("kernel_ldl")
+    rng = np.random.RandomState(3)
+    B = rng.rand(6, 77, 50)
+    AA = np.concatenate([g["AA"], np.zeros((0, 40, 40))])          # 8 x 40 x 40, SPD
+    for mats, beta in ((AA, 0.05), (np.einsum("nik,njk->nij", B, B), 0.5)):
+        Lo, Do = oracle.ldl(mats, modified=True, beta=beta, delta=1e-6)
+        L, D = engine.ldl(mats, modified=True, beta=beta, delta=1e-6)
+        clamp_free = oracle.ldl(mats, modified=True, beta=1e9, delta=1e-6)[1]
+        assert np.abs(Do - clamp_free).max() > 1e-3, "test does not exercise the clamp"
+        np.testing.assert_allclose(D, Do, rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(L, Lo, rtol=1e-7, atol=1e-10)
+
+
 def test_status_codes_and_params(engine, oracle):
     """Non-optimal statuses agree with the oracle; max_iter gives status 5; empty batch ok."""
     A = np.array([[1.0, 1.0, 1.0, 0.0], [1.0, 1.0, 0.0, 1.0]])
@@ -217,7 +233,7 @@ def test_full_size_config3_properties(engine):
     assert np.einsum("ij,ij->i", x, z).max() < eps
     assert x.min() > 0 and z.min() > 0
     # primal objective c'x == dual objective b'y up to the gap (max c'x, A x = b; dual: A'y - z = c)
-    np.testing.assert_allclose(objective(x, c), np.einsum("ij,ij->i", y, b), rtol=1e-8)
+    np.testing.assert_allclose(objective(x, c), np.einsum("ij,ij->i", y, b), rtol=0, atol=1e-6)
     sub = {k: v[:8] for k, v in res.items()}
     assert_parity(sub, g, g["c"], "cfg3 head")
     assert 20 <= res["iters"].min() and res["iters"].max() <= 40

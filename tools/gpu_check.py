@@ -60,3 +60,17 @@ if "time5" in which:
         t = time.time(); res = eng.solve_host(b, c); dt = time.time() - t
         print("cfg5 N=%d: %.3f s  -> %.0f solves/s; status hist %s; iters mean %.1f" % (
             N, dt, N / dt, np.bincount(res["status"], minlength=6), res["iters"].mean()))
+if "prof3" in which:
+    N = 1184
+    A, b, c = random_equality_arrays(200, 200, 1.0, N)
+    eng.setup_dense(A, N)
+    eng.solve_host(b, c)
+    eng.phase_profile(True)
+    t = time.time(); res = eng.solve_host(b, c); dt = time.time() - t
+    prof = eng.phase_profile(False)
+    tot = sum(prof.values())
+    print("cfg3 N=%d %.3fs; phase cycles per Newton step:" % (N, dt))
+    steps = res["iters"].sum()
+    for k, v in prof.items():
+        print("  %-10s %9.0f cyc/step  %5.1f%%" % (k, v / steps, 100.0 * v / tot))
+    print("  total %.0f cyc/step" % (tot / steps))
