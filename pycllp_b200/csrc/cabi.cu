@@ -116,7 +116,7 @@ int finish_setup(pycllp_b200_engine* e, int max_problems) {
   e->sc.slot = slot;
   e->sc.L_in_smem = Ls;
   e->sc.vec_in_smem = Vs;
-  int per_sm = solve_kernel_max_blocks_per_sm(e->smem_bytes);
+  int per_sm = solve_kernel_max_blocks_per_sm(e->smem_bytes, Ls, Vs);
   if (per_sm < 1) return fail(e, PYCLLP_B200_ERR_CUDA, "kernel does not fit on an SM");
   e->grid = std::max(1, std::min(max_problems, e->num_sms * per_sm));
   e->max_problems = max_problems;
@@ -453,7 +453,7 @@ int pycllp_b200_ldl(pycllp_b200_engine* e, int N, int m, const double* AA, doubl
   if (N <= 0 || m <= 0 || !AA || !L || !D) return fail(e, PYCLLP_B200_ERR_ARG, "ldl: bad argument");
   DeviceGuard guard(e->device);
   const size_t lsz = (size_t)m * (m + 1) / 2;
-  const size_t slot = al16((size_t)m * NB + lsz + m);
+  const size_t slot = al16((size_t)m * NB + 512 + lsz + m);
   const int grid = std::min(N, e->num_sms);
   double *d_AA = nullptr, *d_L = nullptr, *d_D = nullptr, *d_s = nullptr;
   cudaError_t err = cudaMalloc(&d_AA, (size_t)N * m * m * sizeof(double));

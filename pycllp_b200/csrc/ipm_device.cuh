@@ -162,7 +162,7 @@ __device__ __forceinline__ void A_times2(const Matrix& A, const double* __restri
 // ---------------------------------------------------------------------------------------
 // M = A diag(d) A'  (full symmetric m x m into W.M), returns nothing; caller syncs.
 // ---------------------------------------------------------------------------------------
-static __device__ void form_M_dense(const Matrix& A, Work& W) {
+static __device__ __forceinline__ void form_M_dense(const Matrix& A, Work& W) {
   const int m = A.m, ldd = A.ldd;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, tg = lane & 3;
@@ -229,7 +229,7 @@ static __device__ void form_M_dense(const Matrix& A, Work& W) {
   }
 }
 
-static __device__ void form_M_sparse(const Matrix& A, Work& W) {
+static __device__ __forceinline__ void form_M_sparse(const Matrix& A, Work& W) {
   const int m = A.m;
   for (int e = threadIdx.x; e < A.nme; e += NT) {
     double s = 0.0;
@@ -247,7 +247,7 @@ static __device__ void form_M_sparse(const Matrix& A, Work& W) {
 //   plain != 0     : ldl.cl:28-55 (no clamping).
 // Left-looking by panels of NB columns, one thread per row.
 // ---------------------------------------------------------------------------------------
-static __device__ void factor_ldl(int m, Work& W, double beta, double delta, int plain) {
+static __device__ __forceinline__ void factor_ldl(int m, Work& W, double beta, double delta, int plain) {
   const int tid = threadIdx.x;
   double* __restrict__ L = W.L;
   double* __restrict__ D = W.D;
@@ -314,7 +314,7 @@ namespace pb200 {
 // ---------------------------------------------------------------------------------------
 // S <- (L D)^-1 S ; S <- L^-T S ; dy += S      (ldl.cl:519-536), warp 0 only (v1, unused).
 // ---------------------------------------------------------------------------------------
-static __device__ void tri_solve(int m, Work& W) {
+static __device__ __forceinline__ void tri_solve(int m, Work& W) {
   if (threadIdx.x < 32) {
     const int lane = threadIdx.x;
     double* __restrict__ S = W.S;
@@ -346,7 +346,7 @@ static __device__ void tri_solve(int m, Work& W) {
 }
 
 // S = RHS - M dy ; returns max |S|   (ldl.cl:577-599)
-static __device__ double residual_M(int m, Work& W) {
+static __device__ __forceinline__ double residual_M(int m, Work& W) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double mx = 0.0;
   for (int i = warp; i < m; i += NWARP) {
@@ -362,7 +362,7 @@ static __device__ double residual_M(int m, Work& W) {
 }
 
 // factor + solve + refinement (ldl.cl:602-653); requires W.d, W.RHS set. Leaves dy.
-static __device__ void solve_normal(const Matrix& A, Work& W, const Params& p) {
+static __device__ __forceinline__ void solve_normal(const Matrix& A, Work& W, const Params& p) {
   const int m = A.m, tid = threadIdx.x;
   long long t0 = phase_begin(W);
   if (A.sparse) form_M_sparse(A, W); else form_M_dense_tma(A, W);
@@ -405,7 +405,7 @@ static __device__ void solve_normal(const Matrix& A, Work& W, const Params& p) {
 
 // Given x, z, y (and mu): v = A'y -> W.w ; t, d ; q -> W.w ; RHS ; also rho/sigma norms.
 // Returns through refs. After this W.t holds t = c - A'y + mu/x (the ONE evaluation).
-static __device__ void prepare_rhs(const Matrix& A, Work& W, double mu, double& normr, double& norms) {
+static __device__ __forceinline__ void prepare_rhs(const Matrix& A, Work& W, double mu, double& normr, double& norms) {
   const int m = A.m, n = A.n, tid = threadIdx.x;
   At_times(A, W.y, W.w);                      // own outputs only: no sync needed before reuse
   double ss = 0.0;
@@ -432,7 +432,7 @@ static __device__ void prepare_rhs(const Matrix& A, Work& W, double mu, double& 
 }
 
 // dx, dz, ratio test, update (primal_normal.cl:122-156) using the stored t.
-static __device__ void step(const Matrix& A, Work& W, double mu, double r) {
+static __device__ __forceinline__ void step(const Matrix& A, Work& W, double mu, double r) {
   const int m = A.m, n = A.n, tid = threadIdx.x;
   At_times(A, W.dy, W.w);
   double th = 0.0;

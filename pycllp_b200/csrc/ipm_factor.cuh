@@ -31,7 +31,7 @@ __device__ __forceinline__ int dbl_hi(double v) { return __double2hiint(v); }
 // Exact, column-by-column elimination of one panel whose updated (unscaled) entries are in
 // L storage; rhs row entries in crhs[]. Used when the speculative path cannot be proven
 // equivalent, and for whole factorizations in "plain" mode by the caller's v1 code.
-static __device__ void panel_exact(int m, int j0, int nb, Work& W, double beta, double delta,
+static __device__ __forceinline__ void panel_exact(int m, int j0, int nb, Work& W, double beta, double delta,
                                    double* crhs, double* Sf, bool with_rhs) {
   const int tid = threadIdx.x;
   double* __restrict__ L = W.L;
@@ -68,9 +68,164 @@ static __device__ void panel_exact(int m, int j0, int nb, Work& W, double beta, 
 // 32-bit packed index: L(i, j) lives at coff(j, m) + i   (valid while m(m+1)/2 < 2^31)
 __device__ __forceinline__ int coff(int j, int m) { return j * (m - 1) - ((j * (j - 1)) >> 1); }
 
+// approximate single-precision reciprocal (one MUFU), seed of rcp_pos
+__device__ __forceinline__ float rcp_approx_f32(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// 1/d to within an ulp for delta <= d < 1e30 (callers guarantee the range): single-precision
+// seed + two Newton steps.
+__device__ __forceinline__ double rcp_pos(double d) {
+  double r = (double)rcp_approx_f32((float)d);
+  double e = fma(-d, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-d, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
+
+// Step B of factor_ldl_fast: eliminate the 8x8 diagonal block of panel j0 (its updated,
+// unscaled entries are in L storage).  Run by ONE warp, and it is the serial bottleneck of the
+// whole factorisation (a lone warp issues a dependent instruction every ~5 cycles), so the
+// instruction stream is kept minimal: the 36 lower-triangle entries are spread over the lanes
+// (entry q = lane, column-major inside the block: column starts 0,8,15,21,26,30,33,35; the
+// four entries 32..35 ride in a second register of lanes 0..3), columns 0..4 are eliminated
+// with two shuffles per entry, the trailing 3x3 block redundantly in every lane.
+// Speculative D_j = max(|D_j|, delta) (theta clamp assumed inactive, checked in step D; a
+// pivot above 1e30 also routes to the exact path).  Outputs, all to shared scratch: D1, rinv,
+// W[j][k] = D_k L11[j][k] (= the unscaled entry), th[] = in-block part of theta_j (hi words),
+// the raw block (for the exact redo); the scaled L11 goes to L storage.
+static __device__ __forceinline__ void diag_block(int m, int j0, int nb, Work& W, double delta,
+                                                  int* th) {
+  const int lane = threadIdx.x & 31;
+  double* __restrict__ L = W.L;
+  double* Wm = W.red + RED_W;
+  double* D1 = W.red + RED_D1;
+  double* rinv = W.red + RED_RINV;
+  double* rawd = W.red + RED_RAWD;
+  const unsigned FULL = 0xffffffffu;
+  // lane -> (row ei, column ej) of entry q = lane
+  const int ej = (lane >= 8) + (lane >= 15) + (lane >= 21) + (lane >= 26) + (lane >= 30);
+  const int cs_mine = (0x1e1a150f0800ull >> (8 * ej)) & 0xff;      // {0,8,15,21,26,30}
+  const int ei = ej + lane - cs_mine;
+  // second entry of lanes 0..3: (7,5) (6,6) (7,6) (7,7)
+  const bool has2 = lane < 4;
+  const int fi = (lane == 1) ? 6 : 7;
+  const int fj = (lane == 0) ? 5 : (lane == 3) ? 7 : 6;
+  const int idx0 = coff(min(j0 + ej, m - 1), m) + j0 + ei;
+  const int idx1 = coff(min(j0 + fj, m - 1), m) + j0 + fi;
+  double e0 = (ei == ej) ? 1.0 : 0.0;
+  double e1 = (has2 && fi == fj) ? 1.0 : 0.0;
+  if (ei < nb) e0 = L[idx0];
+  if (has2 && fi < nb) e1 = L[idx1];
+  rawd[ei * 8 + ej] = e0;
+  if (has2) rawd[fi * 8 + fj] = e1;
+  bool big = false;
+
+#pragma unroll
+  for (int jj = 0; jj < 5; jj++) {
+    const int c0 = (jj == 0) ? 0 : (jj == 1) ? 8 : (jj == 2) ? 15 : (jj == 3) ? 21 : 26;
+    const bool upd = ej > jj;
+    const bool incol = (ej == jj) && (ei > jj);
+    const int srcl = c0 + (upd ? ei - jj : 0), srcw = c0 + (upd ? ej - jj : 0);
+    const double pj = __shfl_sync(FULL, e0, c0);
+    const double li = __shfl_sync(FULL, e0, srcl);
+    const double wj = __shfl_sync(FULL, e0, srcw);
+    const double li2 = __shfl_sync(FULL, e0, c0 + fi - jj);
+    const double wj2 = __shfl_sync(FULL, e0, c0 + fj - jj);
+    const int ht = __reduce_max_sync(FULL, incol ? (dbl_hi(e0) & 0x7fffffff) : 0);
+    const double Dj = fmax(fabs(pj), delta);
+    big |= !(Dj < 1e30);
+    const double r = rcp_pos(Dj);
+    if (upd) e0 = fma(-(li * r), wj, e0);
+    e1 = fma(-(li2 * r), wj2, e1);
+    if (incol) {
+      Wm[ei * 8 + jj] = e0;        // D_j * l_ij == the unscaled entry
+      e0 *= r;
+    }
+    if (lane == c0) {
+      th[jj] = ht;
+      D1[jj] = Dj;
+      rinv[jj] = r;
+    }
+  }
+  // trailing 3x3 block (rows/cols 5..7), redundantly in every lane
+  double b55 = __shfl_sync(FULL, e0, 30), b65 = __shfl_sync(FULL, e0, 31);
+  double b75 = __shfl_sync(FULL, e1, 0), b66 = __shfl_sync(FULL, e1, 1);
+  double b76 = __shfl_sync(FULL, e1, 2), b77 = __shfl_sync(FULL, e1, 3);
+  const double D5 = fmax(fabs(b55), delta);
+  const double r5 = rcp_pos(D5);
+  const int ht5 = max(dbl_hi(b65) & 0x7fffffff, dbl_hi(b75) & 0x7fffffff);
+  const double w65 = b65, w75 = b75;
+  b65 *= r5;
+  b75 *= r5;
+  b66 = fma(-b65, w65, b66);
+  b76 = fma(-b75, w65, b76);
+  b77 = fma(-b75, w75, b77);
+  const double D6 = fmax(fabs(b66), delta);
+  const double r6 = rcp_pos(D6);
+  const int ht6 = dbl_hi(b76) & 0x7fffffff;
+  const double w76 = b76;
+  b76 *= r6;
+  b77 = fma(-b76, w76, b77);
+  const double D7 = fmax(fabs(b77), delta);
+  const double r7 = rcp_pos(D7);
+  big |= !(D5 < 1e30) | !(D6 < 1e30) | !(D7 < 1e30);
+  if (lane == 5) { th[5] = ht5; D1[5] = D5; rinv[5] = r5; Wm[6 * 8 + 5] = w65; Wm[7 * 8 + 5] = w75; }
+  if (lane == 6) { th[6] = ht6; D1[6] = D6; rinv[6] = r6; Wm[7 * 8 + 6] = w76; }
+  if (lane == 7) { th[7] = 0; D1[7] = D7; rinv[7] = r7; if (big) th[0] = 0x7ff00000; }
+  if (lane == 31) e0 = b65;
+  if (lane == 0) e1 = b75;
+  if (lane == 2) e1 = b76;
+  // scaled unit-lower block back to L storage
+  if (ei == ej) e0 = 1.0;
+  if (fi == fj) e1 = 1.0;
+  if (ei < nb) L[idx0] = e0;
+  if (has2 && fi < nb) L[idx1] = e1;
+}
+
+// The inner loop of step A for one warp: acc (8x8, rows ra+0..7 [and ra+drow+0..7]) =
+// sum_k L(row, k) * P[k][:] over k < j0, as DMMAs with two split-K chains per tile.  A lone
+// warp issues roughly one dependent instruction per 5 cycles, so the loop carries nothing but
+// the loads, the DMMAs and three pointer updates; operands of the next iteration are loaded
+// before the DMMAs of the current one.
+template <bool TWO>
+__device__ __forceinline__ void panel_update_tiles(const double* __restrict__ L,
+                                                   const double* __restrict__ P, int m, int j0,
+                                                   int tg, int g, int ra, int drow, double& c0,
+                                                   double& c1, double& u0, double& u1) {
+  double e0 = 0.0, e1 = 0.0, v0 = 0.0, v1 = 0.0;
+  c0 = c1 = u0 = u1 = 0.0;
+  if (j0 == 0) return;
+  const double* pa = L + coff(tg, m) + ra;      // column k = tg, row ra
+  int d = 4 * m - 10 - 4 * tg;                  // coff(k + 4) - coff(k); decreases by 16 per step
+  const double* pb = P + tg * NB + g;
+  double a1, a2, a3 = 0.0, a4 = 0.0, b1, b2;
+  a1 = pa[0]; if (TWO) a3 = pa[drow]; pa += d; d -= 16;
+  a2 = pa[0]; if (TWO) a4 = pa[drow]; pa += d; d -= 16;
+  b1 = pb[0]; b2 = pb[4 * NB]; pb += 8 * NB;
+  for (int k0 = 8; k0 < j0; k0 += 8) {
+    double n1, n2, n3 = 0.0, n4 = 0.0;
+    n1 = pa[0]; if (TWO) n3 = pa[drow]; pa += d; d -= 16;
+    n2 = pa[0]; if (TWO) n4 = pa[drow]; pa += d; d -= 16;
+    const double m1 = pb[0], m2 = pb[4 * NB]; pb += 8 * NB;
+    dmma884(c0, c1, a1, b1);
+    if (TWO) dmma884(u0, u1, a3, b1);
+    dmma884(e0, e1, a2, b2);
+    if (TWO) dmma884(v0, v1, a4, b2);
+    a1 = n1; a2 = n2; a3 = n3; a4 = n4; b1 = m1; b2 = m2;
+  }
+  dmma884(c0, c1, a1, b1);
+  if (TWO) dmma884(u0, u1, a3, b1);
+  dmma884(e0, e1, a2, b2);
+  if (TWO) dmma884(v0, v1, a4, b2);
+  c0 += e0; c1 += e1; u0 += v0; u1 += v1;
+}
+
 // Pre-condition: the lower triangle of M is stored in W.L (packed column-major).
 // rhs != nullptr: also computes Sf = (L D)^-1 rhs.
-static __device__ void factor_ldl_fast(int m, Work& W, double beta, double delta,
+static __device__ __forceinline__ void factor_ldl_fast(int m, Work& W, double beta, double delta,
                                        const double* __restrict__ rhs, double* __restrict__ Sf) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, tg = lane & 3;
@@ -104,40 +259,55 @@ static __device__ void factor_ldl_fast(int m, Work& W, double beta, double delta
     tq = phase_begin(W);
 
     // ---- step A (+ B on warp 0) ----
-    // FP64 FMAs queue behind DMMAs of the same SM sub-partition (measured: a dependent DFMA
-    // chain runs 20x slower next to three DMMA warps, profiles/fp64_latency_r01.txt), so the
-    // latency-critical elimination of the diagonal block (step B) gets sub-partition 0 to
-    // itself: warp 0 updates tile 0 and eliminates it, warp 4 updates the rhs row, and the
-    // twelve warps of sub-partitions 1-3 update all other row tiles.
+    // Measured on B200 (profiles/fp64_latency_r01.txt, dmma_loop_probe_r01.txt): FP64 FMAs
+    // queue behind the DMMAs of their own SM sub-partition (a dependent DFMA chain runs 20x
+    // slower next to three DMMA warps) and a DMMA queues behind every DMMA already issued on
+    // its sub-partition.  So the latency-critical chain  tile 0 -> step B  is kept apart:
+    //   A1. the 8x8 diagonal tile and the rhs row are updated first, split-K over warps 0-3
+    //       and 4-7 (one warp per sub-partition each), while nobody else issues DMMAs;
+    //   A2. warp 0 (alone on sub-partition 0) reduces the partials and eliminates the block
+    //       (step B) while the twelve warps of sub-partitions 1-3 update all other row tiles.
+    double* part = P + (size_t)m * NB;                       // [8][64] split-K partials
+    const int nks = j0 >> 2;                                  // k-steps of 4 columns
+    if (warp < 8 && (warp < 4 || with_rhs)) {
+      const long long t0w = phase_begin(W);
+      const int qw = warp & 3;
+      const bool is_rhs = warp >= 4;
+      const int row = j0 + g;
+      const bool ok = is_rhs ? (g == 0) : (row < m);
+      const int rs = (row < m) ? row : j0;
+      double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
+      for (int ks = qw; ks < nks; ks += 8) {
+        const int ka = 4 * ks + tg, kb = ka + 16;
+        const bool hasb = ks + 4 < nks;
+        double a1 = is_rhs ? Sf[ka] : L[coff(ka, m) + rs];
+        double a2 = hasb ? (is_rhs ? Sf[kb] : L[coff(kb, m) + rs]) : 0.0;
+        const double b1 = P[ka * NB + g];
+        const double b2 = hasb ? P[kb * NB + g] : 0.0;
+        if (!ok) { a1 = 0.0; a2 = 0.0; }
+        dmma884(c0, c1, a1, b1);
+        if (hasb) dmma884(e0, e1, a2, b2);
+      }
+      part[warp * 64 + g * 8 + 2 * tg] = c0 + e0;
+      part[warp * 64 + g * 8 + 2 * tg + 1] = c1 + e1;
+      if (warp == 0) phase_end(W, 12, t0w);
+    }
+    __syncthreads();
     const int wsub = warp & 3;
     if (wsub != 0) {
+      const long long tw = (W.prof && tid == 32) ? clock64() : 0;
       const int widx = (warp >> 2) * 3 + wsub - 1;            // 0..11
       for (int rt0 = 1 + widx; rt0 < ntile; rt0 += 24) {
         const int rt1 = rt0 + 12;
         const bool two = rt1 < ntile;
         const int rowa = j0 + 8 * rt0 + g, rowb = j0 + 8 * rt1 + g;
         const bool oka = rowa < m, okb = two && rowb < m;
-        double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;     // tile rt0: two split-K accumulators
-        double u0 = 0.0, u1 = 0.0, v0 = 0.0, v1 = 0.0;     // tile rt1
-        const int ra = oka ? rowa : j0, rb = okb ? rowb : j0;   // safe rows for the loads
-        int k = tg;
-        int off = coff(k, m);
-        for (int k0 = 0; k0 < j0; k0 += 8) {
-          const int off2 = off + 4 * m - 10 - 4 * k;          // coff(k + 4)
-          const double b1 = P[k * NB + g];
-          const double b2 = P[(k + 4) * NB + g];
-          double a1 = L[off + ra], a2 = L[off2 + ra];
-          double a3 = L[off + rb], a4 = L[off2 + rb];
-          if (!oka) { a1 = 0.0; a2 = 0.0; }
-          if (!okb) { a3 = 0.0; a4 = 0.0; }
-          dmma884(c0, c1, a1, b1);
-          dmma884(u0, u1, a3, b1);
-          dmma884(e0, e1, a2, b2);
-          dmma884(v0, v1, a4, b2);
-          off = off2 + 4 * m - 10 - 4 * (k + 4);              // coff(k + 8)
-          k += 8;
-        }
-        c0 += e0; c1 += e1; u0 += v0; u1 += v1;
+        // rows past the end read row j0 instead (always valid); a DMMA row only feeds the same
+        // row of the result, which is then simply not stored -- no masking in the loop
+        const int ra = oka ? rowa : j0, rb = okb ? rowb : j0;
+        double c0, c1, u0, u1;
+        if (two) panel_update_tiles<true>(L, P, m, j0, tg, g, ra, rb - ra, c0, c1, u0, u1);
+        else panel_update_tiles<false>(L, P, m, j0, tg, g, ra, 0, c0, c1, u0, u1);
 #pragma unroll
         for (int h = 0; h < 2; h++) {
           const int col = 2 * tg + h;
@@ -148,96 +318,28 @@ static __device__ void factor_ldl_fast(int m, Work& W, double beta, double delta
           }
         }
       }
-    } else if (warp == 0 || (warp == 4 && with_rhs)) {
-      // tile 0 (warp 0) / the rhs row (warp 4): four split-K chains to keep the chain short
-      const bool is_rhs = warp == 4;
+      if (W.prof && tid == 32)
+        reinterpret_cast<unsigned long long*>(W.red + RED_PROF)[13] += (unsigned long long)(clock64() - tw);
+    } else if (warp == 0) {
+      // reduce the split-K partials of tile 0, apply, eliminate
       const int row = j0 + g;
-      const bool ok = !is_rhs && row < m;
-      const int rs = ok ? row : j0;
-      double c[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
-      int k = tg;
-      int off = coff(k, m);
-      for (int k0 = 0; k0 < j0; k0 += 16) {
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-          if (k0 + 4 * q < j0) {
-            double a = is_rhs ? Sf[k] : L[off + rs];
-            if (is_rhs ? (g != 0) : !ok) a = 0.0;
-            dmma884(c[q][0], c[q][1], a, P[k * NB + g]);
-          }
-          off += 4 * m - 10 - 4 * k;
-          k += 4;
-        }
-      }
-      const double s0 = (c[0][0] + c[1][0]) + (c[2][0] + c[3][0]);
-      const double s1 = (c[0][1] + c[1][1]) + (c[2][1] + c[3][1]);
 #pragma unroll
       for (int h = 0; h < 2; h++) {
         const int col = 2 * tg + h;
-        if (col < nb) {
-          if (is_rhs) { if (g == 0) crhs[col] = rhs[j0 + col] - (h ? s1 : s0); }
-          else if (ok && row >= j0 + col) L[coff(j0 + col, m) + row] -= (h ? s1 : s0);
-        }
+        const int e = g * 8 + col;
+        const double sum = (part[e] + part[64 + e]) + (part[128 + e] + part[192 + e]);
+        if (col < nb && row < m && row >= j0 + col) L[coff(j0 + col, m) + row] -= sum;
       }
-      if (warp == 0) {
-        // ---- step B: 8x8 diagonal block, every lane of warp 0 redundantly ----
-        __syncwarp();
-        long long tb = phase_begin(W);
-        int cb[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++) cb[j] = coff(min(j0 + j, m - 1), m) + j0;
-        double a[8][8];
-#pragma unroll
-        for (int i = 0; i < 8; i++)
-#pragma unroll
-          for (int j = 0; j <= i; j++)
-            a[i][j] = (i < nb) ? L[cb[j] + i] : (i == j ? 1.0 : 0.0);
-        if (lane < 8) {   // lane i keeps the raw row i for the exact redo
-#pragma unroll
-          for (int i = 0; i < 8; i++)
-            if (lane == i) {
-#pragma unroll
-              for (int j = 0; j <= i; j++) rawd[i * 8 + j] = a[i][j];
-            }
-        }
-#pragma unroll
-        for (int jj = 0; jj < 8; jj++) {
-          double t = 0.0;
-#pragma unroll
-          for (int i = jj + 1; i < 8; i++) t = fmax(t, fabs(a[i][jj]));
-          const double Dj = fmax(fabs(a[jj][jj]), delta);   // speculative: theta clamp inactive
-          const double r = 1.0 / Dj;
-          if (lane == jj) {                                   // spread the stores over lanes
-            if (jj < nb) {
-              atomicMax(&th[jj], dbl_hi(t));
-              D[j0 + jj] = Dj;
-              D1[jj] = Dj;
-              rinv[jj] = r;
-            } else {
-              D1[jj] = 1.0;
-              rinv[jj] = 1.0;
-            }
-          }
-#pragma unroll
-          for (int i = jj + 1; i < 8; i++) a[i][jj] *= r;
-#pragma unroll
-          for (int j2 = jj + 1; j2 < 8; j2++) {
-            const double w = Dj * a[j2][jj];
-            if (lane == 8 + jj) Wm[j2 * 8 + jj] = w;
-#pragma unroll
-            for (int i = j2; i < 8; i++) a[i][j2] -= a[i][jj] * w;
-          }
-        }
-        // lane i (< 8) writes row i of the unit-lower block
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-          if (lane == i && i < nb) {
-#pragma unroll
-            for (int j = 0; j < i; j++) L[cb[j] + i] = a[i][j];
-            L[cb[i] + i] = 1.0;
-          }
-        }
-        phase_end(W, 9, tb);
+      // ---- step B: 8x8 diagonal block on warp 0, one matrix entry per lane ----
+      __syncwarp();
+      long long tb = phase_begin(W);
+      diag_block(m, j0, nb, W, delta, th);
+      phase_end(W, 9, tb);
+    } else if (warp == 4 && with_rhs) {
+      if (lane < 8 && lane < nb) {
+        const int e = lane;   // row g = 0 of the rhs tile
+        const double sum = (part[256 + e] + part[320 + e]) + (part[384 + e] + part[448 + e]);
+        crhs[lane] = rhs[j0 + lane] - sum;
       }
     }
     __syncthreads();
@@ -250,48 +352,36 @@ static __device__ void factor_ldl_fast(int m, Work& W, double beta, double delta
     int hmax[8];
 #pragma unroll
     for (int jj = 0; jj < 8; jj++) hmax[jj] = 0;
-    if (tid < nthr_rows || nthr_rows > NT) {
-      double wreg[28];                                        // W[jj][k], k < jj
-      double rv[8];
-      {
-        int q = 0;
-#pragma unroll
-        for (int jj = 1; jj < 8; jj++)
-#pragma unroll
-          for (int k = 0; k < jj; k++) wreg[q++] = Wm[jj * 8 + k];
-#pragma unroll
-        for (int jj = 0; jj < 8; jj++) rv[jj] = rinv[jj];
-      }
+    if (tid >= NT - 8 && tid - (NT - 8) < nb) D[j0 + tid - (NT - 8)] = D1[tid - (NT - 8)];
+    {
       int cb[8];
 #pragma unroll
       for (int j = 0; j < 8; j++) cb[j] = coff(min(j0 + j, m - 1), m);
       for (int t = tid; t < nthr_rows; t += NT) {
         const bool is_rhs = (t == nbelow);
         const int row = is_rhs ? m - 1 : j0 + 8 + t;
-        double l[8];
+        double c[8];
 #pragma unroll
         for (int jj = 0; jj < 8; jj++) {
           double cv = (jj < nb) ? L[cb[jj] + row] : 0.0;
           if (is_rhs) cv = (jj < nb) ? crhs[jj] : 0.0;
           P[t * 8 + jj] = cv;                                  // kept for the exact redo
-          l[jj] = cv;
+          c[jj] = cv;
         }
-        {
-          int q = 0;
+        // right-looking inside the row: l_k = c_k / D_k, then c_jj -= l_k * (D_k L11[jj][k])
 #pragma unroll
-          for (int jj = 0; jj < 8; jj++) {
-            double v = l[jj];
+        for (int k = 0; k < 8; k++) {
+          if (!is_rhs) hmax[k] = max(hmax[k], dbl_hi(c[k]) & 0x7fffffff);
+          const double lk = c[k] * rinv[k];
 #pragma unroll
-            for (int k = 0; k < jj; k++) v -= l[k] * wreg[q++];
-            if (!is_rhs) hmax[jj] = max(hmax[jj], dbl_hi(fabs(v)));
-            l[jj] = v * rv[jj];
-          }
+          for (int jj = k + 1; jj < 8; jj++) c[jj] -= lk * Wm[jj * 8 + k];
+          c[k] = lk;
         }
 #pragma unroll
         for (int jj = 0; jj < 8; jj++) {
           if (jj < nb) {
-            if (is_rhs) Sf[j0 + jj] = l[jj];
-            else L[cb[jj] + row] = l[jj];
+            if (is_rhs) Sf[j0 + jj] = c[jj];
+            else L[cb[jj] + row] = c[jj];
           }
         }
       }
@@ -310,11 +400,13 @@ static __device__ void factor_ldl_fast(int m, Work& W, double beta, double delta
     tq = phase_begin(W);
 
     // ---- step D: was the speculation exact? ----
-    bool bad = false;
-    for (int jj = 0; jj < nb; jj++) {
+    bool bad;
+    {
+      const int jj = lane & 7;
       // theta_ub > theta : bump the hi-word by one (covers the dropped low word)
       const double tub = __hiloint2double(th[jj] + 1, 0);
-      if (!(tub * tub * inv_beta2 * 1.0000001 <= D1[jj])) bad = true;
+      const bool mine = (jj < nb) && !(tub * tub * inv_beta2 * 1.0000001 <= D1[jj]);
+      bad = __any_sync(0xffffffffu, mine);
     }
     if (bad) {
       // restore the updated-but-uneliminated panel and redo it by the sequential rule
@@ -341,7 +433,7 @@ static __device__ void factor_ldl_fast(int m, Work& W, double beta, double delta
 // S <- L^-T S ; dy += S     (second half of ldl.cl:529-536), blocks of 32 columns:
 // the part of each dot product below the block is a warp-per-column reduction on all
 // warps, the 32x32 triangle is back-substituted by warp 0 in registers with shuffles.
-static __device__ void back_solve_fast(int m, Work& W) {
+static __device__ __forceinline__ void back_solve_fast(int m, Work& W) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double* __restrict__ L = W.L;
   double* __restrict__ S = W.S;
@@ -384,7 +476,7 @@ static __device__ void back_solve_fast(int m, Work& W) {
 
 // S <- (L D)^-1 S   (first half, ldl.cl:519-527); only used by refinement passes -- the
 // first solve of every iteration gets this from factor_ldl_fast.
-static __device__ void fwd_solve_fast(int m, Work& W) {
+static __device__ __forceinline__ void fwd_solve_fast(int m, Work& W) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double* __restrict__ L = W.L;
   double* __restrict__ S = W.S;

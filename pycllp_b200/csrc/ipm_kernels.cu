@@ -6,27 +6,32 @@ namespace pb200 {
 
 __device__ __forceinline__ size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
 
-// Carve the block's working set out of shared memory / its scratch slot.
-static __device__ void carve(const Matrix& A, const Scratch& sc, double* smem, Work& W) {
+// Carve the block's working set out of shared memory / its scratch slot.  LS / VS (factor /
+// vectors in shared memory) are compile-time so that the compiler can prove which pointers
+// are shared and emit LDS/STS with 32-bit addresses instead of generic loads.
+template <bool LS, bool VS>
+static __device__ __forceinline__ void carve(const Matrix& A, const Scratch& sc, double* smem, Work& W) {
   const int m = A.m, n = A.n;
   double* slot = sc.base + (size_t)blockIdx.x * sc.slot;
   size_t o = 0;
   W.red = smem + o; o += RED_SIZE;
-  size_t psz = (size_t)m * NB;
+  size_t psz = (size_t)m * NB + 512;     // panel multipliers + split-K partials (ipm_factor.cuh)
   if (psz < (size_t)2 * SY_KC * A.sy_ldm) psz = (size_t)2 * SY_KC * A.sy_ldm;
   W.P = smem + o; o += align16(psz);
   W.dg = smem + o; o += align16(A.ldd > 0 ? A.ldd : 1);
-  double* v = sc.vec_in_smem ? (smem + o) : (slot + sc.off_vec);
-  if (sc.vec_in_smem) o += align16((size_t)6 * n + 6 * m);
+  double* v;
+  if constexpr (VS) { v = smem + o; o += align16((size_t)6 * n + 6 * m); }
+  else v = slot + sc.off_vec;
   W.x = v; W.z = v + n; W.c = v + 2 * n; W.t = v + 3 * n; W.d = v + 4 * n; W.w = v + 5 * n;
   double* u = v + 6 * (size_t)n;
   W.y = u; W.b = u + m; W.dy = u + 2 * m; W.S = u + 3 * m; W.RHS = u + 4 * m; W.D = u + 5 * m;
-  W.L = sc.L_in_smem ? (smem + o) : (slot + sc.off_L);
+  if constexpr (LS) W.L = smem + o;
+  else W.L = slot + sc.off_L;
   W.M = slot;
   W.prof = sc.prof ? sc.prof + (size_t)blockIdx.x * 16 : nullptr;
 }
 
-static __device__ void ipm_solve_one(const Matrix& A, const Batch& B, Work& W, const Params& p, int q) {
+static __device__ __forceinline__ void ipm_solve_one(const Matrix& A, const Batch& B, Work& W, const Params& p, int q) {
   const int m = A.m, n = A.n, tid = threadIdx.x;
   for (int j = tid; j < n; j += NT) {
     W.c[j] = B.c[(size_t)q * n + j];
@@ -80,12 +85,13 @@ static __device__ void ipm_solve_one(const Matrix& A, const Batch& B, Work& W, c
   __syncthreads();
 }
 
+template <bool LS, bool VS>
 __global__ void __launch_bounds__(NT, 1)
 ipm_solve_kernel(Matrix A, Batch B, Scratch sc, Params p) {
   extern __shared__ __align__(16) double smem[];
   __shared__ int s_next;
   Work W;
-  carve(A, sc, smem, W);
+  carve<LS, VS>(A, sc, smem, W);
   if (W.prof && threadIdx.x < 16) reinterpret_cast<unsigned long long*>(W.red + RED_PROF)[threadIdx.x] = 0;
   if (A.sparse) {   // entries outside the pattern of A A' are never written again
     const size_t mm = (size_t)A.m * A.m;
@@ -115,7 +121,7 @@ ldl_hook_kernel(int N, int m, const double* AA, double* Lout, double* Dout, int 
   const size_t lsz = (size_t)m * (m + 1) / 2;
   W.red = smem;
   W.P = s;
-  W.L = s + (size_t)m * NB;
+  W.L = s + (size_t)m * NB + 512;
   W.D = W.L + lsz;
   W.prof = nullptr;
   for (int q = blockIdx.x; q < N; q += gridDim.x) {
@@ -145,7 +151,7 @@ ldl_hook_kernel(int N, int m, const double* AA, double* Lout, double* Dout, int 
 // ---------------------------------------------------------------------------------------
 size_t smem_doubles(const Matrix& A, int L_in_smem, int vec_in_smem) {
   auto al = [](size_t v) { return (v + 15) & ~(size_t)15; };
-  size_t psz = (size_t)A.m * NB;
+  size_t psz = (size_t)A.m * NB + 512;
   if (psz < (size_t)2 * SY_KC * A.sy_ldm) psz = (size_t)2 * SY_KC * A.sy_ldm;
   size_t o = RED_SIZE + al(psz) + al(A.ldd > 0 ? A.ldd : 1);
   if (vec_in_smem) o += al((size_t)6 * A.n + 6 * A.m);
@@ -153,13 +159,20 @@ size_t smem_doubles(const Matrix& A, int L_in_smem, int vec_in_smem) {
   return o;
 }
 
+typedef void (*solve_kernel_t)(Matrix, Batch, Scratch, Params);
+static solve_kernel_t pick_kernel(int L_in_smem, int vec_in_smem) {
+  if (L_in_smem && vec_in_smem) return ipm_solve_kernel<true, true>;
+  if (vec_in_smem) return ipm_solve_kernel<false, true>;
+  return ipm_solve_kernel<false, false>;
+}
+
 cudaError_t launch_solve(const Matrix& A, const Batch& B, const Scratch& sc, const Params& p,
                          int grid, size_t smem_bytes, cudaStream_t stream) {
-  cudaError_t err = cudaFuncSetAttribute(ipm_solve_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+  solve_kernel_t k = pick_kernel(sc.L_in_smem, sc.vec_in_smem);
+  cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem_bytes);
   if (err != cudaSuccess) return err;
-  ipm_solve_kernel<<<grid, NT, smem_bytes, stream>>>(A, B, sc, p);
+  k<<<grid, NT, smem_bytes, stream>>>(A, B, sc, p);
   return cudaGetLastError();
 }
 
@@ -171,11 +184,11 @@ cudaError_t launch_ldl_hook(int N, int m, const double* AA, double* L, double* D
   return cudaGetLastError();
 }
 
-int solve_kernel_max_blocks_per_sm(size_t smem_bytes) {
+int solve_kernel_max_blocks_per_sm(size_t smem_bytes, int L_in_smem, int vec_in_smem) {
   int nb = 0;
-  cudaFuncSetAttribute(ipm_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       (int)smem_bytes);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ipm_solve_kernel, NT, smem_bytes);
+  solve_kernel_t k = pick_kernel(L_in_smem, vec_in_smem);
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, NT, smem_bytes);
   return nb;
 }
 

@@ -46,7 +46,7 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
       : "memory");
 }
 
-static __device__ void form_M_dense_tma(const Matrix& A, Work& W) {
+static __device__ __forceinline__ void form_M_dense_tma(const Matrix& A, Work& W) {
   const int m = A.m, ldm = A.sy_ldm;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, tg = lane & 3;
