@@ -16,7 +16,7 @@ static __device__ __forceinline__ void carve(const Matrix& A, const Scratch& sc,
   size_t o = 0;
   W.red = smem + o; o += RED_SIZE;
   size_t psz = (size_t)m * NB + 512;     // panel multipliers + split-K partials (ipm_factor.cuh)
-  if (psz < (size_t)2 * SY_KC * A.sy_ldm) psz = (size_t)2 * SY_KC * A.sy_ldm;
+  if (psz < (size_t)SY_STAGES * SY_KC * A.sy_ldm) psz = (size_t)SY_STAGES * SY_KC * A.sy_ldm;
   W.P = smem + o; o += align16(psz);
   W.dg = smem + o; o += align16(A.ldd > 0 ? A.ldd : 1);
   double* v;
@@ -152,7 +152,7 @@ ldl_hook_kernel(int N, int m, const double* AA, double* Lout, double* Dout, int 
 size_t smem_doubles(const Matrix& A, int L_in_smem, int vec_in_smem) {
   auto al = [](size_t v) { return (v + 15) & ~(size_t)15; };
   size_t psz = (size_t)A.m * NB + 512;
-  if (psz < (size_t)2 * SY_KC * A.sy_ldm) psz = (size_t)2 * SY_KC * A.sy_ldm;
+  if (psz < (size_t)SY_STAGES * SY_KC * A.sy_ldm) psz = (size_t)SY_STAGES * SY_KC * A.sy_ldm;
   size_t o = RED_SIZE + al(psz) + al(A.ldd > 0 ? A.ldd : 1);
   if (vec_in_smem) o += al((size_t)6 * A.n + 6 * A.m);
   if (L_in_smem) o += (size_t)A.m * (A.m + 1) / 2;

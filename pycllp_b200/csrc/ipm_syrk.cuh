@@ -15,7 +15,7 @@
 
 namespace pb200 {
 
-constexpr int RED_MBAR = 216;   // two 8-byte mbarriers inside W.red
+constexpr int RED_MBAR = 216;   // 2 x SY_STAGES 8-byte mbarriers inside W.red (216..223)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -46,25 +46,39 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
       : "memory");
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 static __device__ __forceinline__ void form_M_dense_tma(const Matrix& A, Work& W) {
   const int m = A.m, ldm = A.sy_ldm;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, tg = lane & 3;
-  const int nch = A.ldd / SY_KC;
+  const int nch = A.ldd / SY_KC;                     // chunks per pass
+  const int total = nch * A.sy_npass;                // chunks streamed in all (A is re-read per pass)
   const uint32_t chunk_bytes = (uint32_t)(SY_KC * ldm * sizeof(double));
-  double* stage0 = W.P;
-  double* stage1 = W.P + SY_KC * ldm;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(W.red + RED_MBAR);
+  const int stage_doubles = SY_KC * ldm;
+  uint64_t* full = reinterpret_cast<uint64_t*>(W.red + RED_MBAR);
+  uint64_t* empty = full + SY_STAGES;
 
   for (int k = tid; k < A.ldd; k += NT) W.dg[k] = (k < A.nd) ? W.d[A.dcols[k]] : 0.0;
   if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
+#pragma unroll
+    for (int s = 0; s < SY_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], NWARP); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  uint32_t ph0 = 0, ph1 = 0;   // phase parity of the two stage barriers
+  long long tk = phase_begin(W);
+  if (tid == 0) {
+    // the staging area was last touched through the generic proxy (the factorisation's P)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    for (int c = 0; c < SY_STAGES - 1 && c < total; c++) {
+      mbar_expect_tx(&full[c], chunk_bytes);
+      tma_load_1d(W.P + c * stage_doubles, A.sy_A + (size_t)(c % nch) * stage_doubles, chunk_bytes, &full[c]);
+    }
+  }
 
+  int gch = 0;                                        // global chunk counter over both passes
   for (int pass = 0; pass < A.sy_npass; pass++) {
     // this warp's segments: (tile row, first tile col, count)
     int segI[SY_SEG], segJ[SY_SEG], segN[SY_SEG];
@@ -79,22 +93,21 @@ static __device__ __forceinline__ void form_M_dense_tma(const Matrix& A, Work& W
 #pragma unroll
       for (int t = 0; t < SY_CW; t++) acc[s][t][0] = acc[s][t][1] = 0.0;
 
-    if (tid == 0) {
-      // the staging area was last touched through the generic proxy (factor's P / previous pass)
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_expect_tx(&bars[0], chunk_bytes);
-      tma_load_1d(stage0, A.sy_A, chunk_bytes, &bars[0]);
-    }
-    for (int ch = 0; ch < nch; ch++) {
-      const int st = ch & 1;
-      if (tid == 0 && ch + 1 < nch) {
-        uint64_t* nb = &bars[st ^ 1];
-        mbar_expect_tx(nb, chunk_bytes);
-        tma_load_1d(st ? stage0 : stage1, A.sy_A + (size_t)(ch + 1) * SY_KC * ldm, chunk_bytes, nb);
+    for (int ch = 0; ch < nch; ch++, gch++) {
+      const int st = gch % SY_STAGES;
+      if (tid == 0) {
+        // keep SY_STAGES-1 chunks in flight: refill the stage that chunk gch-1 occupied
+        const int c = gch + SY_STAGES - 1;
+        if (c < total) {
+          const int cs = c % SY_STAGES;
+          if (c >= SY_STAGES) mbar_wait(&empty[cs], ((c / SY_STAGES) - 1) & 1);
+          mbar_expect_tx(&full[cs], chunk_bytes);
+          tma_load_1d(W.P + cs * stage_doubles, A.sy_A + (size_t)(c % nch) * stage_doubles,
+                      chunk_bytes, &full[cs]);
+        }
       }
-      if (st == 0) { mbar_wait(&bars[0], ph0); ph0 ^= 1; }
-      else         { mbar_wait(&bars[1], ph1); ph1 ^= 1; }
-      const double* __restrict__ S = st ? stage1 : stage0;
+      mbar_wait(&full[st], (gch / SY_STAGES) & 1);
+      const double* __restrict__ S = W.P + st * stage_doubles;
 #pragma unroll
       for (int ks = 0; ks < SY_KC / 4; ks++) {
         const double dk = W.dg[ch * SY_KC + ks * 4 + tg];
@@ -113,8 +126,11 @@ static __device__ __forceinline__ void form_M_dense_tma(const Matrix& A, Work& W
           }
         }
       }
-      __syncthreads();   // every warp is done with stage st: it may be refilled
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[st]);        // this warp is done with stage st
     }
+    phase_end(W, 14, tk);
+    tk = phase_begin(W);
     // epilogue: tiles -> packed L storage and full M
 #pragma unroll
     for (int s = 0; s < SY_SEG; s++) {
@@ -135,6 +151,8 @@ static __device__ __forceinline__ void form_M_dense_tma(const Matrix& A, Work& W
         }
       }
     }
+    phase_end(W, 15, tk);
+    tk = phase_begin(W);
   }
   __syncthreads();
   // singleton (slack) columns: diagonal only
