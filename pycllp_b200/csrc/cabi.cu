@@ -233,12 +233,19 @@ int pycllp_b200_setup_dense(pycllp_b200_engine* e, int m, int n, const double* A
   for (int i = 0; i < m; i++)
     for (int k = 0; k < M.nd; k++) Ad[(size_t)i * M.ldd + k] = A[(size_t)i * n + dcols[k]];
   dcols.resize(M.ldd, 0);
-  std::vector<int> sptr(m + 1, 0), scol;
-  std::vector<double> sw;
+  std::vector<int> sptr(m + 1, 0), scol, colrow(n, -1);
+  std::vector<double> sw, sa, colval(n, 0.0);
   for (int i = 0; i < m; i++) {
-    for (auto& pr : sing[i]) { scol.push_back(pr.first); sw.push_back(pr.second); }
+    for (auto& pr : sing[i]) {
+      scol.push_back(pr.first);
+      sw.push_back(pr.second);
+      sa.push_back(A[(size_t)i * n + pr.first]);
+      colrow[pr.first] = i;
+      colval[pr.first] = A[(size_t)i * n + pr.first];
+    }
     sptr[i + 1] = (int)scol.size();
   }
+  for (int k = 0; k < M.nd; k++) colrow[dcols[k]] = -2;
   std::vector<double> Ah(A, A + (size_t)m * n);
   // TMA-staged SYRK operand: chunks of SY_KC packed columns, k-major, rows padded to ldm
   // with ldm = 4 (mod 16) so that the four k-rows of a DMMA fragment hit disjoint banks
@@ -280,6 +287,9 @@ int pycllp_b200_setup_dense(pycllp_b200_engine* e, int m, int n, const double* A
   if ((rc = upload(e, sptr, &M.sing_ptr))) return rc;
   if ((rc = upload(e, scol, &M.sing_col))) return rc;
   if ((rc = upload(e, sw, &M.sing_w))) return rc;
+  if ((rc = upload(e, sa, &M.sing_a))) return rc;
+  if ((rc = upload(e, colrow, &M.colrow))) return rc;
+  if ((rc = upload(e, colval, &M.colval))) return rc;
   return finish_setup(e, max_problems);
 }
 

@@ -83,6 +83,7 @@ struct Work {
   double *y, *b, *dy, *S, *RHS, *D;     // m each
   double* P;                            // max(m*NB, 2*TB*LDT): panel multipliers / SYRK tiles
   double* dg;                           // ldd : d gathered on the packed SYRK columns
+  double* g2;                           // ldd : second gather buffer (A_times2)
   double* L;                            // m(m+1)/2 packed column-major
   double* M;                            // m*m full symmetric (global scratch)
   double* red;                          // 256: reductions [0,32) + panel scratch (ipm_factor.cuh)
@@ -102,18 +103,46 @@ __device__ __forceinline__ void phase_end(const Work& W, int id, long long t0) {
 }
 
 // ---------------------------------------------------------------------------------------
-// operator A : v = A' u (n outputs)
+// mat-vecs with the shared matrix.  A lives in L2 (shared by all blocks); a warp takes FOUR
+// rows (or columns) at a time so that ~28 independent loads per lane are in flight and the
+// L2 latency is paid once per four dot products.  Dense mode works on the packed operand
+// (columns of A with >= 2 non-zeros): Ad (m x ldd, row-major) for A u, sy_A (ldd x ldm,
+// column k contiguous) for A' u; singleton columns (slacks) are a single multiply.
 // ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void warp_sum4(double& a0, double& a1, double& a2, double& a3) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    a3 += __shfl_xor_sync(0xffffffffu, a3, o);
+  }
+}
+
+// out = A' u (n outputs).  Ends with __syncthreads().
 __device__ __forceinline__ void At_times(const Matrix& A, const double* __restrict__ u,
                                          double* __restrict__ out) {
   const int m = A.m, n = A.n;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (!A.sparse) {
+    const int ldm = A.sy_ldm;
+    for (int k0 = warp * 4; k0 < A.nd; k0 += NWARP * 4) {      // ldd >= nd rounded up: no guards
+      const double* __restrict__ p = A.sy_A + (size_t)k0 * ldm;
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      for (int i = lane; i < m; i += 32) {
+        const double ui = u[i];
+        a0 += p[i] * ui;
+        a1 += p[ldm + i] * ui;
+        a2 += p[2 * ldm + i] * ui;
+        a3 += p[3 * ldm + i] * ui;
+      }
+      warp_sum4(a0, a1, a2, a3);
+      if (lane < 4 && k0 + lane < A.nd)
+        out[A.dcols[k0 + lane]] = (lane == 0) ? a0 : (lane == 1) ? a1 : (lane == 2) ? a2 : a3;
+    }
     for (int j = threadIdx.x; j < n; j += NT) {
-      double acc = 0.0;
-      const double* __restrict__ col = A.A + j;
-#pragma unroll 4
-      for (int i = 0; i < m; i++) acc += col[(size_t)i * n] * u[i];
-      out[j] = acc;
+      const int r = A.colrow[j];
+      if (r != -2) out[j] = (r >= 0) ? A.colval[j] * u[r] : 0.0;
     }
   } else {
     for (int j = threadIdx.x; j < n; j += NT) {
@@ -122,26 +151,51 @@ __device__ __forceinline__ void At_times(const Matrix& A, const double* __restri
       out[j] = acc;
     }
   }
+  __syncthreads();
 }
 
-// o1 = A u1, o2 = A u2 (m outputs each), one pass over A
+// o1 = A u1, o2 = A u2 (m outputs each), one pass over A.  g1/g2: scratch of ldd doubles
+// (dense mode: u1/u2 gathered onto the packed columns).  Ends with __syncthreads().
 __device__ __forceinline__ void A_times2(const Matrix& A, const double* __restrict__ u1,
                                          const double* __restrict__ u2, double* __restrict__ o1,
-                                         double* __restrict__ o2) {
-  const int m = A.m, n = A.n;
+                                         double* __restrict__ o2, double* __restrict__ g1,
+                                         double* __restrict__ g2) {
+  const int m = A.m;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (!A.sparse) {
-    for (int i = warp; i < m; i += NWARP) {
-      const double* __restrict__ row = A.A + (size_t)i * n;
-      double a1 = 0.0, a2 = 0.0;
-      for (int j = lane; j < n; j += 32) {
-        double a = row[j];
-        a1 += a * u1[j];
-        a2 += a * u2[j];
+    const int ldd = A.ldd;
+    for (int k = threadIdx.x; k < ldd; k += NT) {
+      const bool ok = k < A.nd;
+      const int j = ok ? A.dcols[k] : 0;
+      g1[k] = ok ? u1[j] : 0.0;
+      g2[k] = ok ? u2[j] : 0.0;
+    }
+    __syncthreads();
+    for (int i0 = warp * 2; i0 < m; i0 += NWARP * 2) {
+      const bool two = i0 + 1 < m;
+      const double* __restrict__ ra = A.Ad + (size_t)i0 * ldd;
+      const double* __restrict__ rb = A.Ad + (size_t)(two ? i0 + 1 : i0) * ldd;
+      double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+      for (int k = lane; k < ldd; k += 32) {
+        const double x = g1[k], q = g2[k], va = ra[k], vb = rb[k];
+        a0 += va * x;
+        a1 += va * q;
+        b0 += vb * x;
+        b1 += vb * q;
       }
-      a1 = warp_sum(a1);
-      a2 = warp_sum(a2);
-      if (lane == 0) { o1[i] = a1; o2[i] = a2; }
+      warp_sum4(a0, a1, b0, b1);
+      if (lane < 2 && (lane == 0 || two)) {
+        const int i = i0 + lane;
+        double s1 = lane ? b0 : a0, s2 = lane ? b1 : a1;
+        for (int e = A.sing_ptr[i]; e < A.sing_ptr[i + 1]; e++) {
+          const double a = A.sing_a[e];
+          const int j = A.sing_col[e];
+          s1 += a * u1[j];
+          s2 += a * u2[j];
+        }
+        o1[i] = s1;
+        o2[i] = s2;
+      }
     }
   } else {
     for (int i = warp; i < m; i += NWARP) {
@@ -157,6 +211,7 @@ __device__ __forceinline__ void A_times2(const Matrix& A, const double* __restri
       if (lane == 0) { o1[i] = a1; o2[i] = a2; }
     }
   }
+  __syncthreads();
 }
 
 // ---------------------------------------------------------------------------------------
@@ -345,18 +400,31 @@ static __device__ __forceinline__ void tri_solve(int m, Work& W) {
   __syncthreads();
 }
 
-// S = RHS - M dy ; returns max |S|   (ldl.cl:577-599)
+// S = RHS - M dy ; returns max |S|   (ldl.cl:577-599); M is the block's full symmetric copy
+// in its L2-resident scratch slot, four rows per warp at a time.
 static __device__ __forceinline__ double residual_M(int m, Work& W) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double mx = 0.0;
-  for (int i = warp; i < m; i += NWARP) {
-    const double* __restrict__ row = W.M + (size_t)i * m;
-    double acc = 0.0;
-    for (int j = lane; j < m; j += 32) acc += row[j] * W.dy[j];
-    acc = warp_sum(acc);
-    double r = W.RHS[i] - acc;
-    if (lane == 0) W.S[i] = r;
-    mx = fmax(mx, fabs(r));
+  for (int i0 = warp * 4; i0 < m; i0 += NWARP * 4) {
+    const double* __restrict__ r0 = W.M + (size_t)i0 * m;
+    const double* __restrict__ r1 = W.M + (size_t)min(i0 + 1, m - 1) * m;
+    const double* __restrict__ r2 = W.M + (size_t)min(i0 + 2, m - 1) * m;
+    const double* __restrict__ r3 = W.M + (size_t)min(i0 + 3, m - 1) * m;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    for (int j = lane; j < m; j += 32) {
+      const double v = W.dy[j];
+      a0 += r0[j] * v;
+      a1 += r1[j] * v;
+      a2 += r2[j] * v;
+      a3 += r3[j] * v;
+    }
+    warp_sum4(a0, a1, a2, a3);
+    if (lane < 4 && i0 + lane < m) {
+      const double acc = (lane == 0) ? a0 : (lane == 1) ? a1 : (lane == 2) ? a2 : a3;
+      const double r = W.RHS[i0 + lane] - acc;
+      W.S[i0 + lane] = r;
+      mx = fmax(mx, fabs(r));
+    }
   }
   return block_max(mx, W.red);
 }
@@ -407,7 +475,7 @@ static __device__ __forceinline__ void solve_normal(const Matrix& A, Work& W, co
 // Returns through refs. After this W.t holds t = c - A'y + mu/x (the ONE evaluation).
 static __device__ __forceinline__ void prepare_rhs(const Matrix& A, Work& W, double mu, double& normr, double& norms) {
   const int m = A.m, n = A.n, tid = threadIdx.x;
-  At_times(A, W.y, W.w);                      // own outputs only: no sync needed before reuse
+  At_times(A, W.y, W.w);
   double ss = 0.0;
   for (int j = tid; j < n; j += NT) {
     double v = W.w[j], xj = W.x[j], zj = W.z[j], cj = W.c[j];
@@ -420,8 +488,7 @@ static __device__ __forceinline__ void prepare_rhs(const Matrix& A, Work& W, dou
   }
   norms = sqrt(block_sum(ss, W.red));          // (syncs: t, d, q visible)
   // S <- A x ; RHS <- A q
-  A_times2(A, W.x, W.w, W.S, W.RHS);
-  __syncthreads();
+  A_times2(A, W.x, W.w, W.S, W.RHS, W.dg, W.g2);
   double rr = 0.0;
   for (int i = tid; i < m; i += NT) {
     double rho = W.b[i] - W.S[i];

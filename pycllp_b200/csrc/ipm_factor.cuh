@@ -122,6 +122,7 @@ static __device__ __forceinline__ void diag_block(int m, int j0, int nb, Work& W
   rawd[ei * 8 + ej] = e0;
   if (has2) rawd[fi * 8 + fj] = e1;
   bool big = false;
+  const int hdelta = dbl_hi(delta);
 
 #pragma unroll
   for (int jj = 0; jj < 5; jj++) {
@@ -135,8 +136,10 @@ static __device__ __forceinline__ void diag_block(int m, int j0, int nb, Work& W
     const double li2 = __shfl_sync(FULL, e0, c0 + fi - jj);
     const double wj2 = __shfl_sync(FULL, e0, c0 + fj - jj);
     const int ht = __reduce_max_sync(FULL, incol ? (dbl_hi(e0) & 0x7fffffff) : 0);
-    const double Dj = fmax(fabs(pj), delta);
-    big |= !(Dj < 1e30);
+    // D_j = max(|pivot|, delta) decided on the high words (ties, NaN and huge pivots -> exact path)
+    const int hp = dbl_hi(pj) & 0x7fffffff;
+    big |= (hp == hdelta) | (hp >= 0x46293e59);                  // 0x46293e59 ~ hi word of 1e30
+    const double Dj = (hp < hdelta) ? delta : fabs(pj);
     const double r = rcp_pos(Dj);
     if (upd) e0 = fma(-(li * r), wj, e0);
     e1 = fma(-(li2 * r), wj2, e1);
@@ -365,7 +368,7 @@ static __device__ __forceinline__ void factor_ldl_fast(int m, Work& W, double be
         for (int jj = 0; jj < 8; jj++) {
           double cv = (jj < nb) ? L[cb[jj] + row] : 0.0;
           if (is_rhs) cv = (jj < nb) ? crhs[jj] : 0.0;
-          P[t * 8 + jj] = cv;                                  // kept for the exact redo
+          P[jj * nthr_rows + t] = cv;                          // kept for the exact redo (conflict-free)
           c[jj] = cv;
         }
         // right-looking inside the row: l_k = c_k / D_k, then c_jj -= l_k * (D_k L11[jj][k])
@@ -418,8 +421,8 @@ static __device__ __forceinline__ void factor_ldl_fast(int m, Work& W, double be
         const bool is_rhs = (t == nbelow);
         const int row = j0 + 8 + t;
         for (int jj = 0; jj < nb; jj++) {
-          if (is_rhs) crhs[jj] = P[(size_t)t * 8 + jj];
-          else L[cidx(row, j0 + jj, m)] = P[(size_t)t * 8 + jj];
+          if (is_rhs) crhs[jj] = P[jj * nthr_rows + t];
+          else L[cidx(row, j0 + jj, m)] = P[jj * nthr_rows + t];
         }
       }
       __syncthreads();

@@ -19,6 +19,7 @@ static __device__ __forceinline__ void carve(const Matrix& A, const Scratch& sc,
   if (psz < (size_t)SY_STAGES * SY_KC * A.sy_ldm) psz = (size_t)SY_STAGES * SY_KC * A.sy_ldm;
   W.P = smem + o; o += align16(psz);
   W.dg = smem + o; o += align16(A.ldd > 0 ? A.ldd : 1);
+  W.g2 = smem + o; o += align16(A.ldd > 0 ? A.ldd : 1);
   double* v;
   if constexpr (VS) { v = smem + o; o += align16((size_t)6 * n + 6 * m); }
   else v = slot + sc.off_vec;
@@ -153,7 +154,7 @@ size_t smem_doubles(const Matrix& A, int L_in_smem, int vec_in_smem) {
   auto al = [](size_t v) { return (v + 15) & ~(size_t)15; };
   size_t psz = (size_t)A.m * NB + 512;
   if (psz < (size_t)SY_STAGES * SY_KC * A.sy_ldm) psz = (size_t)SY_STAGES * SY_KC * A.sy_ldm;
-  size_t o = RED_SIZE + al(psz) + al(A.ldd > 0 ? A.ldd : 1);
+  size_t o = RED_SIZE + al(psz) + 2 * al(A.ldd > 0 ? A.ldd : 1);
   if (vec_in_smem) o += al((size_t)6 * A.n + 6 * A.m);
   if (L_in_smem) o += (size_t)A.m * (A.m + 1) / 2;
   return o;

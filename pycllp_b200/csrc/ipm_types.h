@@ -39,6 +39,11 @@ struct Matrix {
   const int* sing_ptr;     // [m+1]
   const int* sing_col;     // original column index
   const double* sing_w;    // a^2
+  const double* sing_a;    // a
+  // per column j: colrow[j] = -2 general (>= 2 non-zeros), -1 empty, else the row of its only
+  // non-zero colval[j]
+  const int* colrow;
+  const double* colval;
   // sparse operator: CSR of A and of A'
   const int *Ap, *Ai;
   const double* Ax;
