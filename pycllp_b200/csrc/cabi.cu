@@ -100,7 +100,7 @@ size_t al16(size_t v) { return (v + 15) & ~(size_t)15; }
 // choose the shared-memory configuration, the grid and allocate scratch + staging
 int finish_setup(pycllp_b200_engine* e, int max_problems) {
   const int m = e->A.m, n = e->A.n;
-  const size_t limit = e->smem_optin - 1024;   // static smem + margin
+  const size_t limit = e->smem_optin - 128;    // static smem (16 B) + margin
   int Ls = 1, Vs = 1;
   if (smem_doubles(e->A, 1, 1) * 8 > limit) { Ls = 0; }
   if (smem_doubles(e->A, Ls, 1) * 8 > limit) { Vs = 0; }
@@ -463,7 +463,7 @@ int pycllp_b200_ldl(pycllp_b200_engine* e, int N, int m, const double* AA, doubl
   if (N <= 0 || m <= 0 || !AA || !L || !D) return fail(e, PYCLLP_B200_ERR_ARG, "ldl: bad argument");
   DeviceGuard guard(e->device);
   const size_t lsz = (size_t)m * (m + 1) / 2;
-  const size_t slot = al16((size_t)m * NB + 512 + lsz + m);
+  const size_t slot = al16((size_t)2 * m * NB + 512 + lsz + m);
   const int grid = std::min(N, e->num_sms);
   double *d_AA = nullptr, *d_L = nullptr, *d_D = nullptr, *d_s = nullptr;
   cudaError_t err = cudaMalloc(&d_AA, (size_t)N * m * m * sizeof(double));

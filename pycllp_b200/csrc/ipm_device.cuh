@@ -32,6 +32,11 @@ namespace pb200 {
 // ---------------------------------------------------------------------------------------
 // small helpers
 // ---------------------------------------------------------------------------------------
+// Warp index as a value the compiler KNOWS to be warp-uniform (broadcast from lane 0).  With
+// the plain threadIdx.x >> 5 every `if (warp == ...)` is treated as potentially divergent and
+// each __shfl_sync / mma.sync inside it is wrapped in WARPSYNC.COLLECTIVE ... ENDCOLLECTIVE
+// (measured: the 8x8 pivot block ran 6x slower that way).
+__device__ __forceinline__ int warp_id() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -44,24 +49,24 @@ __device__ __forceinline__ double warp_max(double v) {
 }
 // Deterministic block reductions; every thread gets the result. red: >= 32 doubles.
 __device__ __forceinline__ double block_sum(double v, double* red) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, warp = warp_id();
   v = warp_sum(v);
   if (lane == 0) red[warp] = v;
   __syncthreads();
   double r = (lane < NWARP) ? red[lane] : 0.0;
   r = warp_sum(r);
   __syncthreads();
-  return r;
+  return __shfl_sync(0xffffffffu, r, 0);     // provably warp-uniform (loop exits depend on it)
 }
 __device__ __forceinline__ double block_max(double v, double* red) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, warp = warp_id();
   v = warp_max(v);
   if (lane == 0) red[warp] = v;
   __syncthreads();
   double r = (lane < NWARP) ? red[lane] : 0.0;   // all callers reduce non-negative values
   r = warp_max(r);
   __syncthreads();
-  return r;
+  return __shfl_sync(0xffffffffu, r, 0);     // provably warp-uniform
 }
 
 // packed lower triangle, COLUMN-major: column j holds rows j..m-1 contiguously, so that a
@@ -94,12 +99,17 @@ struct Work {
 // Counters accumulate in shared memory (W.red[224..240)) and are flushed once per kernel,
 // so that reading the clock does not put a global round trip on the critical path.
 constexpr int RED_PROF = 224;
+// (Every thread reads the clock -- a branch on threadIdx.x == 0 here would make the code that
+// follows look divergent to the compiler and to the hardware.)
 __device__ __forceinline__ long long phase_begin(const Work& W) {
-  return (W.prof && threadIdx.x == 0) ? clock64() : 0;
+  return W.prof ? clock64() : 0;
 }
 __device__ __forceinline__ void phase_end(const Work& W, int id, long long t0) {
-  if (W.prof && threadIdx.x == 0)
-    reinterpret_cast<unsigned long long*>(W.red + RED_PROF)[id] += (unsigned long long)(clock64() - t0);
+  if (W.prof) {
+    const unsigned long long dt = (unsigned long long)(clock64() - t0);
+    unsigned long long* slot = reinterpret_cast<unsigned long long*>(W.red + RED_PROF) + id;
+    if (threadIdx.x == 0) *slot += dt;
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -123,7 +133,7 @@ __device__ __forceinline__ void warp_sum4(double& a0, double& a1, double& a2, do
 __device__ __forceinline__ void At_times(const Matrix& A, const double* __restrict__ u,
                                          double* __restrict__ out) {
   const int m = A.m, n = A.n;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, warp = warp_id();
   if (!A.sparse) {
     const int ldm = A.sy_ldm;
     for (int k0 = warp * 4; k0 < A.nd; k0 += NWARP * 4) {      // ldd >= nd rounded up: no guards
@@ -161,7 +171,7 @@ __device__ __forceinline__ void A_times2(const Matrix& A, const double* __restri
                                          double* __restrict__ o2, double* __restrict__ g1,
                                          double* __restrict__ g2) {
   const int m = A.m;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, warp = warp_id();
   if (!A.sparse) {
     const int ldd = A.ldd;
     for (int k = threadIdx.x; k < ldd; k += NT) {
@@ -219,7 +229,7 @@ __device__ __forceinline__ void A_times2(const Matrix& A, const double* __restri
 // ---------------------------------------------------------------------------------------
 static __device__ __forceinline__ void form_M_dense(const Matrix& A, Work& W) {
   const int m = A.m, ldd = A.ldd;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = warp_id();
   const int g = lane >> 2, tg = lane & 3;
   const int wr = warp >> 2, wc = warp & 3;
   double* As = W.P;
@@ -403,7 +413,7 @@ static __device__ __forceinline__ void tri_solve(int m, Work& W) {
 // S = RHS - M dy ; returns max |S|   (ldl.cl:577-599); M is the block's full symmetric copy
 // in its L2-resident scratch slot, four rows per warp at a time.
 static __device__ __forceinline__ double residual_M(int m, Work& W) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, warp = warp_id();
   double mx = 0.0;
   for (int i0 = warp * 4; i0 < m; i0 += NWARP * 4) {
     const double* __restrict__ r0 = W.M + (size_t)i0 * m;
@@ -430,6 +440,7 @@ static __device__ __forceinline__ double residual_M(int m, Work& W) {
 }
 
 // factor + solve + refinement (ldl.cl:602-653); requires W.d, W.RHS set. Leaves dy.
+template <bool LS>
 static __device__ __forceinline__ void solve_normal(const Matrix& A, Work& W, const Params& p) {
   const int m = A.m, tid = threadIdx.x;
   long long t0 = phase_begin(W);
@@ -450,7 +461,18 @@ static __device__ __forceinline__ void solve_normal(const Matrix& A, Work& W, co
   for (int i = tid; i < m; i += NT) W.dy[i] = 0.0;
   __syncthreads();
   phase_end(W, 6, t0);
-  factor_ldl_fast(m, W, beta, p.ldl_delta, W.RHS, W.S);   // also S <- (L D)^-1 RHS
+  bool redo = true;
+  if (LS && m <= 8 * 35) redo = factor_ldl_pipe(m, W, beta, p.ldl_delta, W.RHS, W.S);
+  if (redo) {
+    if (LS && m <= 8 * 35) {     // speculation failed somewhere: restore M and take the exact-capable path
+      for (int e = tid; e < m * m; e += NT) {
+        const int j = e / m, i = e - j * m;
+        if (i >= j) W.L[cidx(i, j, m)] = W.M[(size_t)j * m + i];
+      }
+      __syncthreads();
+    }
+    factor_ldl_fast(m, W, beta, p.ldl_delta, W.RHS, W.S);   // also S <- (L D)^-1 RHS
+  }
   phase_end(W, 2, t0);
   t0 = phase_begin(W);
   back_solve_fast(m, W);

@@ -15,11 +15,11 @@ static __device__ __forceinline__ void carve(const Matrix& A, const Scratch& sc,
   double* slot = sc.base + (size_t)blockIdx.x * sc.slot;
   size_t o = 0;
   W.red = smem + o; o += RED_SIZE;
-  size_t psz = (size_t)m * NB + 512;     // panel multipliers + split-K partials (ipm_factor.cuh)
+  size_t psz = (size_t)2 * m * NB + 512; // two panel-multiplier tables + split-K partials (ipm_factor.cuh)
   if (psz < (size_t)SY_STAGES * SY_KC * A.sy_ldm) psz = (size_t)SY_STAGES * SY_KC * A.sy_ldm;
   W.P = smem + o; o += align16(psz);
   W.dg = smem + o; o += align16(A.ldd > 0 ? A.ldd : 1);
-  W.g2 = smem + o; o += align16(A.ldd > 0 ? A.ldd : 1);
+  W.g2 = W.P;      // second gather buffer of A_times2: the panel/stage area is idle then
   double* v;
   if constexpr (VS) { v = smem + o; o += align16((size_t)6 * n + 6 * m); }
   else v = slot + sc.off_vec;
@@ -32,6 +32,7 @@ static __device__ __forceinline__ void carve(const Matrix& A, const Scratch& sc,
   W.prof = sc.prof ? sc.prof + (size_t)blockIdx.x * 16 : nullptr;
 }
 
+template <bool LS>
 static __device__ __forceinline__ void ipm_solve_one(const Matrix& A, const Batch& B, Work& W, const Params& p, int q) {
   const int m = A.m, n = A.n, tid = threadIdx.x;
   for (int j = tid; j < n; j += NT) {
@@ -48,7 +49,7 @@ static __device__ __forceinline__ void ipm_solve_one(const Matrix& A, const Batc
   if (B.hook) {   // one solve_primal_normal (ldl.cl:602-653) on the given state
     double nr, ns;
     prepare_rhs(A, W, B.mu, nr, ns);
-    solve_normal(A, W, p);
+    solve_normal<LS>(A, W, p);
     for (int i = tid; i < m; i += NT) B.dy_out[(size_t)q * m + i] = W.dy[i];
     __syncthreads();
     return;
@@ -69,7 +70,7 @@ static __device__ __forceinline__ void ipm_solve_one(const Matrix& A, const Batc
     if (normr < p.eps && norms < p.eps && gamma < p.eps) { stat = 0; break; }   // :256-259
     if (normr > 10 * normr0 && normr > p.eps) { stat = 2; break; }              // :261-264
     if (norms > 10 * norms0 && norms > p.eps) { stat = 4; break; }              // :266-269
-    solve_normal(A, W, p);
+    solve_normal<LS>(A, W, p);
     t0 = phase_begin(W);
     step(A, W, mu, p.r);
     phase_end(W, 5, t0);
@@ -102,10 +103,10 @@ ipm_solve_kernel(Matrix A, Batch B, Scratch sc, Params p) {
   for (;;) {
     if (threadIdx.x == 0) s_next = atomicAdd(sc.counter, 1);
     __syncthreads();
-    const int q = s_next;
+    const int q = __shfl_sync(0xffffffffu, s_next, 0);   // warp-uniform for the compiler
     __syncthreads();
     if (q >= B.N) break;
-    ipm_solve_one(A, B, W, p, q);
+    ipm_solve_one<LS>(A, B, W, p, q);
   }
   if (W.prof && threadIdx.x < 16)
     W.prof[threadIdx.x] += reinterpret_cast<unsigned long long*>(W.red + RED_PROF)[threadIdx.x];
@@ -122,7 +123,7 @@ ldl_hook_kernel(int N, int m, const double* AA, double* Lout, double* Dout, int 
   const size_t lsz = (size_t)m * (m + 1) / 2;
   W.red = smem;
   W.P = s;
-  W.L = s + (size_t)m * NB + 512;
+  W.L = s + (size_t)2 * m * NB + 512;
   W.D = W.L + lsz;
   W.prof = nullptr;
   for (int q = blockIdx.x; q < N; q += gridDim.x) {
@@ -152,9 +153,9 @@ ldl_hook_kernel(int N, int m, const double* AA, double* Lout, double* Dout, int 
 // ---------------------------------------------------------------------------------------
 size_t smem_doubles(const Matrix& A, int L_in_smem, int vec_in_smem) {
   auto al = [](size_t v) { return (v + 15) & ~(size_t)15; };
-  size_t psz = (size_t)A.m * NB + 512;
+  size_t psz = (size_t)2 * A.m * NB + 512;
   if (psz < (size_t)SY_STAGES * SY_KC * A.sy_ldm) psz = (size_t)SY_STAGES * SY_KC * A.sy_ldm;
-  size_t o = RED_SIZE + al(psz) + 2 * al(A.ldd > 0 ? A.ldd : 1);
+  size_t o = RED_SIZE + al(psz) + al(A.ldd > 0 ? A.ldd : 1);
   if (vec_in_smem) o += al((size_t)6 * A.n + 6 * A.m);
   if (L_in_smem) o += (size_t)A.m * (A.m + 1) / 2;
   return o;

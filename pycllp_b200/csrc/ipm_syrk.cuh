@@ -52,7 +52,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 
 static __device__ __forceinline__ void form_M_dense_tma(const Matrix& A, Work& W) {
   const int m = A.m, ldm = A.sy_ldm;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = warp_id();
   const int g = lane >> 2, tg = lane & 3;
   const int nch = A.ldd / SY_KC;                     // chunks per pass
   const int total = nch * A.sy_npass;                // chunks streamed in all (A is re-read per pass)
@@ -85,7 +85,9 @@ static __device__ __forceinline__ void form_M_dense_tma(const Matrix& A, Work& W
 #pragma unroll
     for (int s = 0; s < SY_SEG; s++) {
       const int4 e = A.sy_seg[(pass * NWARP + warp) * SY_SEG + s];
-      segI[s] = e.x; segJ[s] = e.y; segN[s] = e.z;
+      segI[s] = __shfl_sync(0xffffffffu, e.x, 0);      // broadcast: known warp-uniform
+      segJ[s] = __shfl_sync(0xffffffffu, e.y, 0);
+      segN[s] = __shfl_sync(0xffffffffu, e.z, 0);
     }
     double acc[SY_SEG][SY_CW][2];
 #pragma unroll

@@ -11,8 +11,8 @@ constexpr int NB = 8;            // LDL' panel width
 constexpr int TB = 64;           // SYRK macro tile (TB x TB outputs per pass)
 constexpr int KC = 16;           // SYRK k-chunk staged in shared memory
 constexpr int LDT = KC + 4;      // padded leading dimension of a staged tile (conflict-free)
-constexpr int SY_KC = 4;         // TMA-staged SYRK: packed columns per chunk
-constexpr int SY_STAGES = 4;     //   chunks in flight (ring of shared-memory stages)
+constexpr int SY_KC = 8;         // TMA-staged SYRK: packed columns per chunk
+constexpr int SY_STAGES = 2;     //   chunks in flight (ring of shared-memory stages)
 constexpr int SY_SEG = 3;        //   segments per warp per pass
 constexpr int SY_CW = 4;         //   8x8 tiles per segment
 
