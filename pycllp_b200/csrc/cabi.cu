@@ -113,6 +113,10 @@ int finish_setup(pycllp_b200_engine* e, int max_problems) {
   if (!Ls) slot += al16(lsz);
   e->sc.off_vec = slot;
   if (!Vs) slot += al16((size_t)6 * n + 6 * m);
+  e->sc.off_P = slot;
+  if (!Vs) slot += al16(work_area_doubles(e->A));
+  e->sc.off_dg = slot;
+  if (!Vs) slot += al16(e->A.ldd > 0 ? e->A.ldd : 1);
   e->sc.slot = slot;
   e->sc.L_in_smem = Ls;
   e->sc.vec_in_smem = Vs;

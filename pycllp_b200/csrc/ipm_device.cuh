@@ -89,6 +89,7 @@ struct Work {
   double* P;                            // max(m*NB, 2*TB*LDT): panel multipliers / SYRK tiles
   double* dg;                           // ldd : d gathered on the packed SYRK columns
   double* g2;                           // ldd : second gather buffer (A_times2)
+  double* tiles;                        // 2*TB*LDT : staging of the macro-tile SYRK (large problems only)
   double* L;                            // m(m+1)/2 packed column-major
   double* M;                            // m*m full symmetric (global scratch)
   double* red;                          // 256: reductions [0,32) + panel scratch (ipm_factor.cuh)
@@ -232,8 +233,8 @@ static __device__ __forceinline__ void form_M_dense(const Matrix& A, Work& W) {
   const int tid = threadIdx.x, lane = tid & 31, warp = warp_id();
   const int g = lane >> 2, tg = lane & 3;
   const int wr = warp >> 2, wc = warp & 3;
-  double* As = W.P;
-  double* Bs = W.P + TB * LDT;
+  double* As = W.tiles;
+  double* Bs = W.tiles + TB * LDT;
   for (int k = tid; k < ldd; k += NT) W.dg[k] = (k < A.nd) ? W.d[A.dcols[k]] : 0.0;
   const int nmt = (m + TB - 1) / TB;
   for (int I = 0; I < nmt; I++) {
@@ -440,11 +441,13 @@ static __device__ __forceinline__ double residual_M(int m, Work& W) {
 }
 
 // factor + solve + refinement (ldl.cl:602-653); requires W.d, W.RHS set. Leaves dy.
-template <bool LS>
+template <bool LS, bool VS>
 static __device__ __forceinline__ void solve_normal(const Matrix& A, Work& W, const Params& p) {
   const int m = A.m, tid = threadIdx.x;
   long long t0 = phase_begin(W);
-  if (A.sparse) form_M_sparse(A, W); else form_M_dense_tma(A, W);
+  if (A.sparse) form_M_sparse(A, W);
+  else if (VS) form_M_dense_tma(A, W);      // operand staged by TMA, needs the shared work area
+  else form_M_dense(A, W);                  // large problems: macro-tile SYRK, 20 KB of staging
   __syncthreads();
   phase_end(W, 1, t0);
   t0 = phase_begin(W);
@@ -452,7 +455,7 @@ static __device__ __forceinline__ void solve_normal(const Matrix& A, Work& W, co
   for (int i = tid; i < m; i += NT) bmax = fmax(bmax, fabs(W.M[(size_t)i * m + i]));
   const double beta = sqrt(block_max(bmax, W.red));
   // the factorisation works in place on the packed lower triangle (the dense SYRK wrote it)
-  if (A.sparse) {
+  if (A.sparse || !VS) {
     for (int e = tid; e < m * m; e += NT) {
       const int j = e / m, i = e - j * m;
       if (i >= j) W.L[cidx(i, j, m)] = W.M[(size_t)j * m + i];

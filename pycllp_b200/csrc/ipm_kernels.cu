@@ -17,12 +17,19 @@ static __device__ __forceinline__ void carve(const Matrix& A, const Scratch& sc,
   W.red = smem + o; o += RED_SIZE;
   size_t psz = (size_t)2 * m * NB + 512; // two panel-multiplier tables + split-K partials (ipm_factor.cuh)
   if (psz < (size_t)SY_STAGES * SY_KC * A.sy_ldm) psz = (size_t)SY_STAGES * SY_KC * A.sy_ldm;
-  W.P = smem + o; o += align16(psz);
-  W.dg = smem + o; o += align16(A.ldd > 0 ? A.ldd : 1);
-  W.g2 = W.P;      // second gather buffer of A_times2: the panel/stage area is idle then
   double* v;
-  if constexpr (VS) { v = smem + o; o += align16((size_t)6 * n + 6 * m); }
-  else v = slot + sc.off_vec;
+  if constexpr (VS) {
+    W.P = smem + o; o += align16(psz);
+    W.dg = smem + o; o += align16(A.ldd > 0 ? A.ldd : 1);
+    W.tiles = nullptr;
+    v = smem + o; o += align16((size_t)6 * n + 6 * m);
+  } else {   // large problems: only the reduction scratch and the SYRK macro tiles stay on-chip
+    W.tiles = smem + o; o += 2 * TB * LDT;
+    W.P = slot + sc.off_P;
+    W.dg = slot + sc.off_dg;
+    v = slot + sc.off_vec;
+  }
+  W.g2 = W.P;      // second gather buffer of A_times2: the panel/stage area is idle then
   W.x = v; W.z = v + n; W.c = v + 2 * n; W.t = v + 3 * n; W.d = v + 4 * n; W.w = v + 5 * n;
   double* u = v + 6 * (size_t)n;
   W.y = u; W.b = u + m; W.dy = u + 2 * m; W.S = u + 3 * m; W.RHS = u + 4 * m; W.D = u + 5 * m;
@@ -32,7 +39,7 @@ static __device__ __forceinline__ void carve(const Matrix& A, const Scratch& sc,
   W.prof = sc.prof ? sc.prof + (size_t)blockIdx.x * 16 : nullptr;
 }
 
-template <bool LS>
+template <bool LS, bool VS>
 static __device__ __forceinline__ void ipm_solve_one(const Matrix& A, const Batch& B, Work& W, const Params& p, int q) {
   const int m = A.m, n = A.n, tid = threadIdx.x;
   for (int j = tid; j < n; j += NT) {
@@ -49,7 +56,7 @@ static __device__ __forceinline__ void ipm_solve_one(const Matrix& A, const Batc
   if (B.hook) {   // one solve_primal_normal (ldl.cl:602-653) on the given state
     double nr, ns;
     prepare_rhs(A, W, B.mu, nr, ns);
-    solve_normal<LS>(A, W, p);
+    solve_normal<LS, VS>(A, W, p);
     for (int i = tid; i < m; i += NT) B.dy_out[(size_t)q * m + i] = W.dy[i];
     __syncthreads();
     return;
@@ -70,7 +77,7 @@ static __device__ __forceinline__ void ipm_solve_one(const Matrix& A, const Batc
     if (normr < p.eps && norms < p.eps && gamma < p.eps) { stat = 0; break; }   // :256-259
     if (normr > 10 * normr0 && normr > p.eps) { stat = 2; break; }              // :261-264
     if (norms > 10 * norms0 && norms > p.eps) { stat = 4; break; }              // :266-269
-    solve_normal<LS>(A, W, p);
+    solve_normal<LS, VS>(A, W, p);
     t0 = phase_begin(W);
     step(A, W, mu, p.r);
     phase_end(W, 5, t0);
@@ -106,7 +113,7 @@ ipm_solve_kernel(Matrix A, Batch B, Scratch sc, Params p) {
     const int q = __shfl_sync(0xffffffffu, s_next, 0);   // warp-uniform for the compiler
     __syncthreads();
     if (q >= B.N) break;
-    ipm_solve_one<LS>(A, B, W, p, q);
+    ipm_solve_one<LS, VS>(A, B, W, p, q);
   }
   if (W.prof && threadIdx.x < 16)
     W.prof[threadIdx.x] += reinterpret_cast<unsigned long long*>(W.red + RED_PROF)[threadIdx.x];
@@ -153,12 +160,20 @@ ldl_hook_kernel(int N, int m, const double* AA, double* Lout, double* Dout, int 
 // ---------------------------------------------------------------------------------------
 size_t smem_doubles(const Matrix& A, int L_in_smem, int vec_in_smem) {
   auto al = [](size_t v) { return (v + 15) & ~(size_t)15; };
-  size_t psz = (size_t)2 * A.m * NB + 512;
-  if (psz < (size_t)SY_STAGES * SY_KC * A.sy_ldm) psz = (size_t)SY_STAGES * SY_KC * A.sy_ldm;
-  size_t o = RED_SIZE + al(psz) + al(A.ldd > 0 ? A.ldd : 1);
-  if (vec_in_smem) o += al((size_t)6 * A.n + 6 * A.m);
+  size_t o = RED_SIZE;
+  if (vec_in_smem) {
+    o += al(work_area_doubles(A)) + al(A.ldd > 0 ? A.ldd : 1) + al((size_t)6 * A.n + 6 * A.m);
+  } else {
+    o += 2 * TB * LDT;
+  }
   if (L_in_smem) o += (size_t)A.m * (A.m + 1) / 2;
   return o;
+}
+
+size_t work_area_doubles(const Matrix& A) {
+  size_t psz = (size_t)2 * A.m * NB + 512;
+  if (psz < (size_t)SY_STAGES * SY_KC * A.sy_ldm) psz = (size_t)SY_STAGES * SY_KC * A.sy_ldm;
+  return psz;
 }
 
 typedef void (*solve_kernel_t)(Matrix, Batch, Scratch, Params);

@@ -73,6 +73,8 @@ struct Scratch {
   size_t slot;        // doubles per slot
   size_t off_L;       // offset of L inside the slot (if not in smem)
   size_t off_vec;     // offset of the vectors inside the slot (if not in smem)
+  size_t off_P;       // offset of the panel work area and of dg (if the vectors are not in smem)
+  size_t off_dg;
   int* counter;       // work counter
   int L_in_smem, vec_in_smem;
   unsigned long long* prof;   // optional [grid][8] per-phase cycle counters (null = off)

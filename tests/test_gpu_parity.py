@@ -249,3 +249,35 @@ def test_repeat_solves_are_cold_starts_and_deterministic(engine):
         assert np.array_equal(r1[k], r2[k])
     r3 = engine.solve_host(g["b"][:5], g["c"][:5])      # N < max_problems
     assert np.array_equal(r3["x"], r1["x"][:5])
+
+
+def test_large_problems_out_of_shared_memory(engine, oracle):
+    """Sizes where the factor (and then the vectors / work area) no longer fit in shared
+    memory and live in the block's global scratch slot: m=520 dense against the oracle,
+    m=1100 n=2600 sparse (config-4 shape, scaled) against the dense engine path and the
+    optimality conditions."""
+    from pycllp_b200.problems import random_equality_arrays, sparse_equality_arrays
+    A, b, c = random_equality_arrays(520, 300, 0.5, 3, seed=4)
+    engine.setup_dense(A, 3)
+    assert not engine.info()["factor_in_smem"]
+    res = engine.solve_host(b, c)
+    ref = oracle.solve_dense(A, b, c)
+    assert_parity(res, ref, c, "dense m=520")
+
+    As, b, c = sparse_equality_arrays(1100, 1500, 0.01, 4, seed=2)
+    engine.setup_sparse(As, 4)
+    info = engine.info()
+    assert not info["factor_in_smem"] and info["smem_bytes"] < 64 * 1024
+    rs = engine.solve_host(b, c)
+    Ad = As.toarray()
+    engine.setup_dense(Ad, 4)
+    rd = engine.solve_host(b, c)
+    np.testing.assert_array_equal(rs["status"], rd["status"])
+    assert (rs["status"] == 0).all()
+    eps = float(np.float32(1e-7))
+    for r in (rs, rd):
+        assert np.linalg.norm(b - r["x"] @ Ad.T, axis=1).max() < eps
+        assert np.linalg.norm(c - r["y"] @ Ad + r["z"], axis=1).max() < eps
+        assert np.einsum("ij,ij->i", r["x"], r["z"]).max() < eps
+    np.testing.assert_allclose(objective(rs["x"], c), objective(rd["x"], c), rtol=1e-8)
+    np.testing.assert_allclose(rs["x"], rd["x"], rtol=1e-6, atol=1e-6)
