@@ -12,6 +12,8 @@ form, synthetic, generator = examples/random_problem.py):
                     configs[2], "dense LDL' path on 1 B200"); weak scaling over ranks
     cfg5            dense random LP m=500 n=1000, 65536/8 = 8192 problems per GPU
     cfg1            examples/random_problem.py m=50 n=100, 64 problems (parity-test size)
+    cfg4            sparse random LP m=2000 n=5000 (1 % density + slacks), 1024 problems per GPU,
+                    sparse solver path (CSR mat-vecs, pattern-based M, dense packed factor)
 
 Timed quantities
     value   solves/s with b, c already resident in HBM (device-pointer C-ABI entry), CUDA
@@ -39,6 +41,7 @@ WORKLOADS = {
     "cfg3": dict(m=200, n0=200, density=1.0, batch=4096),
     "cfg5": dict(m=500, n0=500, density=1.0, batch=8192),
     "cfg1": dict(m=50, n0=50, density=0.1, batch=64),
+    "cfg4": dict(m=2000, n0=3000, density=0.01, batch=1024, sparse=True),
 }
 METRIC = "batched_lp_solves_per_sec"
 
@@ -58,9 +61,14 @@ def make_problem(name, rank, batch=None):
     return A, b, c
 
 
-def flops_per_iteration(m, n):
+def flops_per_iteration(m, n, A=None):
     """M = A D A' lower triangle (m^2 n) + LDL' (m^3/3) + one forward/back
-    solve (2 m^2) + the four mat-vecs with A (8 m n)."""
+    solve (2 m^2) + the four mat-vecs with A (8 m n).  Sparse A: M costs 2 sum_k c_k(c_k+1)/2
+    (c_k = non-zeros of column k), the mat-vecs 8 nnz(A); the factor of A A' is ~dense at the
+    config-4 shape and is counted as m^3/3."""
+    if A is not None:
+        ck = (A != 0).sum(axis=0).astype(np.float64)
+        return float((ck * (ck + 1)).sum()) + m ** 3 / 3.0 + 2.0 * m * m + 8.0 * float((A != 0).sum())
     return m * m * n + m ** 3 / 3.0 + 2.0 * m * m + 8.0 * m * n
 
 
@@ -104,7 +112,7 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_rate(A, b, c, nproblems, threads):
+def cpu_reference_rate(A, b, c, nproblems, threads, sparse=False):
     """Reference CPU path = the reference's own kernels compiled as C (oracle/_ref), else the
     oracle port; process all `nproblems` with `threads` host threads, return (solves/s, kind)."""
     from oracle.bindings import Reference, Oracle
@@ -113,7 +121,8 @@ def cpu_reference_rate(A, b, c, nproblems, threads):
     else:
         impl, kind = Oracle(), "port"
     t0 = time.perf_counter()
-    r = impl.solve_dense(A, b[:nproblems], c[:nproblems], nthreads=threads)
+    solve = impl.solve_sparse if sparse else impl.solve_dense
+    r = solve(A, b[:nproblems], c[:nproblems], nthreads=threads)
     dt = time.perf_counter() - t0
     return nproblems / dt, kind, dt, r
 
@@ -134,12 +143,17 @@ def run_reference_arm(args, rank, world):
         return
     A, b, c = make_problem(args.workload, 0, batch=max(os.cpu_count() or 1, 1) * 2)
     cores = os.cpu_count() or 1
-    sample = cores * (1 if WORKLOADS[args.workload]["m"] >= 200 else 2)
+    wl = WORKLOADS[args.workload]
+    sparse = bool(wl.get("sparse"))
+    sample = cores * (1 if wl["m"] >= 200 else 2)
+    if wl["m"] >= 1000:
+        sample = 1        # minutes per LP on one core at config 4: one LP per step is the bounded sample
     for _ in range(min(args.warmup, 1)):
-        cpu_reference_rate(A, b, c, min(sample, 2), cores)
+        if wl["m"] < 1000:
+            cpu_reference_rate(A, b, c, min(sample, 2), cores, sparse)
     times = []
     for _ in range(args.steps):
-        rate, kind, dt, _ = cpu_reference_rate(A, b, c, sample, cores)
+        rate, kind, dt, _ = cpu_reference_rate(A, b, c, sample, cores, sparse)
         times.append(dt)
     total = sum(times)
     value = sample * args.steps / total
@@ -192,7 +206,11 @@ def main():
     A, b, c = make_problem(args.workload, rank, batch=N)
 
     eng = Engine(local)
-    eng.setup_dense(A, N)
+    if w.get("sparse"):
+        from scipy.sparse import csr_matrix
+        eng.setup_sparse(csr_matrix(A), N)
+    else:
+        eng.setup_dense(A, N)
     info = eng.info()
 
     f64 = torch.float64
@@ -275,7 +293,7 @@ def main():
     if rank == 0:
         value = world * N * args.steps / total_s
         peak, peak_src = fp64_peak()
-        flops_per_step = flops_per_iteration(m, n) * (total_iters / world)   # per launch (= per rank)
+        flops_per_step = flops_per_iteration(m, n, A if w.get("sparse") else None) * (total_iters / world)
         ms_kernel = float(np.mean(step_ms))
         achieved = flops_per_step / (ms_kernel * 1e-3) / 1e12
         line = {
@@ -302,7 +320,12 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
             sample = cores * (2 if m >= 200 else 8)
-            rate, kind, dt, _ = cpu_reference_rate(A, b, c, min(sample, N), cores)
+            if m >= 1000:
+                sample = 0      # config 4: minutes per LP on a core; see `--impl reference`
+            if sample:
+                rate, kind, dt, _ = cpu_reference_rate(A, b, c, min(sample, N), cores, bool(w.get("sparse")))
+            else:
+                rate, kind, dt = None, "reference", 0.0
             line["cpu_baseline"] = {
                 "value": rate, "unit": "solves/s", "cores": cores, "kind": kind,
                 "sample": "first %d LPs of the workload, %d host threads, %.1f s wall"

@@ -97,12 +97,9 @@ __device__ __forceinline__ double rcp_pos(double d) {
 // W[j][k] = D_k L11[j][k] (= the unscaled entry), th[] = in-block part of theta_j (hi words),
 // the raw block (for the exact redo); the scaled L11 goes to L storage.
 static __device__ __forceinline__ void diag_block(int m, int j0, int nb, Work& W, double delta,
-                                                  int* th) {
+                                                  int* th, double* Wm, double* D1, double* rinv) {
   const int lane = threadIdx.x & 31;
   double* __restrict__ L = W.L;
-  double* Wm = W.red + RED_W;
-  double* D1 = W.red + RED_D1;
-  double* rinv = W.red + RED_RINV;
   double* rawd = W.red + RED_RAWD;
   const unsigned FULL = 0xffffffffu;
   // lane -> (row ei, column ej) of entry q = lane
@@ -338,7 +335,7 @@ static __device__ __forceinline__ void factor_ldl_fast(int m, Work& W, double be
       // ---- step B: 8x8 diagonal block on warp 0, one matrix entry per lane ----
       __syncwarp();
       long long tb = phase_begin(W);
-      diag_block(m, j0, nb, W, delta, th);
+      diag_block(m, j0, nb, W, delta, th, Wm, D1, rinv);
       phase_end(W, 9, tb);
     } else if (warp == 4 && with_rhs) {
       if (lane < 8 && lane < nb) {
@@ -539,7 +536,7 @@ static __device__ __forceinline__ bool factor_ldl_pipe(int m, Work& W, double be
     long long tq = phase_begin(W);
     if (warp == 0) {
       const long long tb = phase_begin(W);
-      diag_block(m, j0, nb, W, delta, th);
+      diag_block(m, j0, nb, W, delta, th, Wm, D1, rinv);
       phase_end(W, 9, tb);
 #ifndef PB200_EXPERIMENT_NO_OLD
     } else if (isK && more && j0 > 0) {
@@ -548,15 +545,23 @@ static __device__ __forceinline__ bool factor_ldl_pipe(int m, Work& W, double be
 #endif
       const long long tw = W.prof ? clock64() : 0;
       const double* PB = ((p + 1) & 1) ? PB1 : PB0;
-#pragma unroll
-      for (int s = 0; s < 3; s++) {
-        const int u = widx + 12 * s;
-        if (u <= nt1) {
-          const bool is_rhs = (u == nt1);
-          const int row = j1 + 8 * u + g;
-          const int rs = (!is_rhs && row < m) ? row : j1;
-          pipe_old_unit(L, PB, Sf, m, j0, tg, g, rs, is_rhs, acc[s][0], acc[s][1]);
-        }
+      // units widx and widx+12 share their B fragments (two tiles per k-step), widx+24 alone;
+      // the rhs row (unit nt1) goes through the generic loop
+      const int u0 = widx, u1 = widx + 12, u2 = widx + 24;
+      const int r0 = j1 + 8 * u0 + g, r1 = j1 + 8 * u1 + g, r2 = j1 + 8 * u2 + g;
+      const int s0 = (r0 < m) ? r0 : j1, s1 = (r1 < m) ? r1 : j1, s2 = (r2 < m) ? r2 : j1;
+      if (u1 < nt1) {
+        panel_update_tiles<true>(L, PB, m, j0, tg, g, s0, s1 - s0, acc[0][0], acc[0][1], acc[1][0], acc[1][1]);
+      } else {
+        double d0, d1;
+        if (u0 < nt1) panel_update_tiles<false>(L, PB, m, j0, tg, g, s0, 0, acc[0][0], acc[0][1], d0, d1);
+        else if (u0 == nt1) pipe_old_unit(L, PB, Sf, m, j0, tg, g, j1, true, acc[0][0], acc[0][1]);
+        if (u1 == nt1) pipe_old_unit(L, PB, Sf, m, j0, tg, g, j1, true, acc[1][0], acc[1][1]);
+      }
+      if (u2 <= nt1) {
+        double d0, d1;
+        if (u2 < nt1) panel_update_tiles<false>(L, PB, m, j0, tg, g, s2, 0, acc[2][0], acc[2][1], d0, d1);
+        else pipe_old_unit(L, PB, Sf, m, j0, tg, g, j1, true, acc[2][0], acc[2][1]);
       }
       if (W.prof) {
         const unsigned long long dt = (unsigned long long)(clock64() - tw);

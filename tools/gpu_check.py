@@ -74,3 +74,14 @@ if "prof3" in which:
     for k, v in prof.items():
         print("  %-10s %9.0f cyc/step  %5.1f%%" % (k, v / steps, 100.0 * v / tot))
     print("  total %.0f cyc/step" % (tot / steps))
+if "time4" in which:
+    N = int(os.environ.get("N4", "148"))
+    A, b, c = sparse_equality_arrays(2000, 3000, 0.01, N, seed=0)
+    t = time.time(); eng.setup_sparse(A, N); print("cfg4 setup %.2fs" % (time.time() - t), eng.info())
+    t = time.time(); res = eng.solve_host(b, c); dt = time.time() - t
+    print("cfg4 N=%d: %.3f s  -> %.1f solves/s; status hist %s; iters mean %.1f" % (
+        N, dt, N / dt, np.bincount(res["status"], minlength=6), res["iters"].mean()))
+    Ad = A.toarray()
+    print(" max |b-Ax| %.2e  max |c-A'y+z| %.2e  max gap %.2e" % (
+        np.linalg.norm(b - res["x"] @ Ad.T, axis=1).max(), np.linalg.norm(c - res["y"] @ Ad + res["z"], axis=1).max(),
+        np.einsum("ij,ij->i", res["x"], res["z"]).max()))
