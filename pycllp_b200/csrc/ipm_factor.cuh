@@ -660,19 +660,31 @@ static __device__ __forceinline__ bool factor_ldl_pipe(int m, Work& W, double be
             }
           }
         }
-      } else {
-        // warps 0, 4, 8, 12: multipliers of the OLD loops of panel p+2
-        if (p + 2 < np) {
-          const int j2 = j0 + 16;
-          const int nb2 = min(NB, m - j2);
-          double* PBn = (p & 1) ? PB1 : PB0;
+      }
+      if (tid < 8) thbuf[((p + 1) & 1) * 8 + tid] = 0;
+      // multipliers of the OLD loops of panel p+2: D_k L(j0+16+jj, k), k < j0+8 (rows of block
+      // p+2 were finished in S2): a few entries per thread, warps 0/4/8/12 start right away
+      if (p + 2 < np) {
+        const int j2 = j0 + 16;
+        const int nb2 = min(NB, m - j2);
+        double* PBn = (p & 1) ? PB1 : PB0;
+        // sub-partition-0 warps take the first half of the table, the DMMA warps (after their
+        // two DMMAs per tile) the second half
+        const int total = j1 * NB;
+        const int half = (total / 2) & ~7;
+        if (!isK) {
           const int t4 = (warp >> 2) * 32 + lane;            // 0..127
-          for (int e = t4; e < j1 * NB; e += 128) {
+          for (int e = t4; e < half; e += 128) {
+            const int k = e >> 3, jj = e & 7;
+            PBn[e] = (jj < nb2) ? L[coff(k, m) + j2 + jj] * D[k] : 0.0;
+          }
+        } else {
+          const int t12 = widx * 32 + lane;                  // 0..383
+          for (int e = half + t12; e < total; e += 384) {
             const int k = e >> 3, jj = e & 7;
             PBn[e] = (jj < nb2) ? L[coff(k, m) + j2 + jj] * D[k] : 0.0;
           }
         }
-        if (tid < 8) thbuf[((p + 1) & 1) * 8 + tid] = 0;
       }
     }
     __syncthreads();
