@@ -138,6 +138,17 @@ def fp64_peak():
         return 37.0, "fallback (nominal B200 FP64 ~37 TFLOP/s)"
 
 
+def measured_traffic(workload, nproblems):
+    """DRAM bytes per launch from the committed ncu capture (config 3 only), else None."""
+    if workload != "cfg3":
+        return None
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        return float(d["dram_bytes_per_lp"]) * nproblems
+    except Exception:
+        return None
+
+
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
@@ -313,7 +324,10 @@ def main():
                     "d2h_bytes_per_step": N * (2 * n + m) * 8 + N * 8},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "kernel": "ipm_solve_kernel", "achieved": achieved,
-                         "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                         "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "traffic": measured_traffic(args.workload, N),
+                         "traffic_note": "DRAM bytes per launch (ncu dram__bytes_read+write per LP x LPs); "
+                                         "algorithmic bytes per launch = %d" % (N * ((m + n) * 8 + (2 * n + m) * 8 + 8)),
                          "peak_source": "FP64 DMMA " + peak_src,
                          "flops_model": "sum_p (m^2 n + m^3/3 + 2 m^2 + 8 m n) * newton_steps_p"},
         }
