@@ -108,7 +108,9 @@ static __device__ __forceinline__ void form_M_dense_tma(const Matrix& A, Work& W
                       chunk_bytes, &full[cs]);
         }
       }
+#ifndef PB200_EXPERIMENT_NOWAIT
       mbar_wait(&full[st], (gch / SY_STAGES) & 1);
+#endif
       const double* __restrict__ S = W.P + st * stage_doubles;
 #pragma unroll
       for (int ks = 0; ks < SY_KC / 4; ks++) {

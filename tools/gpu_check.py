@@ -85,3 +85,17 @@ if "time4" in which:
     print(" max |b-Ax| %.2e  max |c-A'y+z| %.2e  max gap %.2e" % (
         np.linalg.norm(b - res["x"] @ Ad.T, axis=1).max(), np.linalg.norm(c - res["y"] @ Ad + res["z"], axis=1).max(),
         np.einsum("ij,ij->i", res["x"], res["z"]).max()))
+if "prof5" in which:
+    N = 296
+    A, b, c = random_equality_arrays(500, 500, 1.0, N)
+    eng.setup_dense(A, N)
+    print(eng.info())
+    eng.solve_host(b[:148], c[:148])
+    eng.phase_profile(True)
+    t = time.time(); res = eng.solve_host(b, c); dt = time.time() - t
+    prof = eng.phase_profile(False)
+    steps = res["iters"].sum()
+    tot = sum(v for k, v in prof.items() if k in ("rhs_norms", "form_M", "factor", "tri_solve", "residual", "step"))
+    print("cfg5 N=%d %.3fs (%.0f solves/s); phase cycles per Newton step:" % (N, dt, N / dt))
+    for k, v in prof.items():
+        print("  %-14s %10.0f cyc/step  %5.1f%%" % (k, v / steps, 100.0 * v / tot))
