@@ -100,7 +100,7 @@ size_t al16(size_t v) { return (v + 15) & ~(size_t)15; }
 // choose the shared-memory configuration, the grid and allocate scratch + staging
 int finish_setup(pycllp_b200_engine* e, int max_problems) {
   const int m = e->A.m, n = e->A.n;
-  const size_t limit = e->smem_optin - 128;    // static smem (16 B) + margin
+  const size_t limit = e->smem_optin - 64;     // static smem (16 B) + margin
   int Ls = 1, Vs = 1;
   if (smem_doubles(e->A, 1, 1) * 8 > limit) { Ls = 0; }
   if (smem_doubles(e->A, Ls, 1) * 8 > limit) { Vs = 0; }
@@ -112,7 +112,7 @@ int finish_setup(pycllp_b200_engine* e, int max_problems) {
   e->sc.off_L = slot;
   if (!Ls) slot += al16(lsz);
   e->sc.off_vec = slot;
-  if (!Vs) slot += al16((size_t)6 * n + 6 * m);
+  if (!Vs) slot += al16(vec_area_doubles(e->A));
   e->sc.off_P = slot;
   if (!Vs) slot += al16(work_area_doubles(e->A));
   e->sc.off_dg = slot;

@@ -10,10 +10,10 @@
 // constants, same stop rule, same modified LDL', same refinement rule):
 //   primal_normal.cl:201-284  standard_primal_normal          -> ipm_solve_one
 //   primal_normal.cl:30-120   primal/dual infeasibility       -> stage "residual norms"
-//   ldl.cl:110-138,280-294    A (X/Z) A' entries, beta        -> form_M_* (once/iteration)
-//   ldl.cl:314-378            factor_primal_normal            -> factor_ldl
+//   ldl.cl:110-138,280-294    A (X/Z) A' entries, beta        -> form_M_dense_tma (ipm_syrk.cuh) / form_M_* (once/iteration)
+//   ldl.cl:314-378            factor_primal_normal            -> factor_ldl_pipe / factor_ldl_fast (ipm_factor.cuh)
 //   ldl.cl:198-219            primal_normal_rhs_i             -> RHS from the stored t
-//   ldl.cl:505-537            forward_backward_primal_normal  -> tri_solve
+//   ldl.cl:505-537            forward_backward_primal_normal  -> forward part inside factor_ldl_*, back_solve_fast
 //   ldl.cl:577-599            residual_primal_normal          -> residual_M
 //   ldl.cl:602-653            solve_primal_normal             -> solve_normal
 //   primal_normal.cl:122-156  primal_normal_step              -> step
@@ -88,7 +88,8 @@ struct Work {
   double *y, *b, *dy, *S, *RHS, *D;     // m each
   double* P;                            // max(m*NB, 2*TB*LDT): panel multipliers / SYRK tiles
   double* dg;                           // ldd : d gathered on the packed SYRK columns
-  double* g2;                           // ldd : second gather buffer (A_times2)
+  double* g1;                           // ldd : gather buffers of A_times2 (alias the work area)
+  double* g2;
   double* tiles;                        // 2*TB*LDT : staging of the macro-tile SYRK (large problems only)
   double* L;                            // m(m+1)/2 packed column-major
   double* M;                            // m*m full symmetric (global scratch)
@@ -114,9 +115,10 @@ __device__ __forceinline__ void phase_end(const Work& W, int id, long long t0) {
 }
 
 // ---------------------------------------------------------------------------------------
-// mat-vecs with the shared matrix.  A lives in L2 (shared by all blocks); a warp takes FOUR
-// rows (or columns) at a time so that ~28 independent loads per lane are in flight and the
-// L2 latency is paid once per four dot products.  Dense mode works on the packed operand
+// mat-vecs with the shared matrix.  A lives in L2 (shared by all blocks); a warp takes four
+// rows x two vectors (or eight columns) at a time so that many independent loads per lane are
+// in flight and the L2 latency is paid once per eight dot products, which are then reduced
+// together (warp_sum8).  Dense mode works on the packed operand
 // (columns of A with >= 2 non-zeros): Ad (m x ldd, row-major) for A u, sy_A (ldd x ldm,
 // column k contiguous) for A' u; singleton columns (slacks) are a single multiply.
 // ---------------------------------------------------------------------------------------
@@ -129,6 +131,30 @@ __device__ __forceinline__ void warp_sum4(double& a0, double& a1, double& a2, do
     a3 += __shfl_xor_sync(0xffffffffu, a3, o);
   }
 }
+// Eight warp-wide sums with 9 shuffles instead of 40: each exchange step halves the number
+// of values a lane still carries.  Returns the total of v[q], q = (lane >> 2) & 7, in every
+// lane of the group of four lanes that share q.
+__device__ __forceinline__ double warp_sum8(const double (&v)[8], int lane) {
+  const unsigned FULL = 0xffffffffu;
+  double w[4], u[2];
+  const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const double send = h16 ? v[i] : v[4 + i];
+    const double keep = h16 ? v[4 + i] : v[i];
+    w[i] = keep + __shfl_xor_sync(FULL, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; i++) {
+    const double send = h8 ? w[i] : w[2 + i];
+    const double keep = h8 ? w[2 + i] : w[i];
+    u[i] = keep + __shfl_xor_sync(FULL, send, 8);
+  }
+  double t = (h4 ? u[1] : u[0]) + __shfl_xor_sync(FULL, h4 ? u[0] : u[1], 4);
+  t += __shfl_xor_sync(FULL, t, 2);
+  t += __shfl_xor_sync(FULL, t, 1);
+  return t;
+}
 
 // out = A' u (n outputs).  Ends with __syncthreads().
 __device__ __forceinline__ void At_times(const Matrix& A, const double* __restrict__ u,
@@ -137,21 +163,28 @@ __device__ __forceinline__ void At_times(const Matrix& A, const double* __restri
   const int lane = threadIdx.x & 31, warp = warp_id();
   if (!A.sparse) {
     const int ldm = A.sy_ldm;
-    for (int k0 = warp * 4; k0 < A.nd; k0 += NWARP * 4) {      // ldd >= nd rounded up: no guards
+    // singleton/empty columns: fetch the table entries now, use them after the packed loop
+    const int jt = threadIdx.x;
+    int r0 = -2;
+    double cv0 = 0.0;
+    if (jt < n) { r0 = A.colrow[jt]; cv0 = A.colval[jt]; }
+    const int q = (lane >> 2) & 7;
+    for (int k0 = warp * 8; k0 < A.nd; k0 += NWARP * 8) {      // ldd >= nd rounded up to 16: no guards
       const double* __restrict__ p = A.sy_A + (size_t)k0 * ldm;
-      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      double a[8];
+#pragma unroll
+      for (int c = 0; c < 8; c++) a[c] = 0.0;
+#pragma unroll 2
       for (int i = lane; i < m; i += 32) {
         const double ui = u[i];
-        a0 += p[i] * ui;
-        a1 += p[ldm + i] * ui;
-        a2 += p[2 * ldm + i] * ui;
-        a3 += p[3 * ldm + i] * ui;
+#pragma unroll
+        for (int c = 0; c < 8; c++) a[c] += p[c * ldm + i] * ui;
       }
-      warp_sum4(a0, a1, a2, a3);
-      if (lane < 4 && k0 + lane < A.nd)
-        out[A.dcols[k0 + lane]] = (lane == 0) ? a0 : (lane == 1) ? a1 : (lane == 2) ? a2 : a3;
+      const double t = warp_sum8(a, lane);
+      if ((lane & 3) == 0 && k0 + q < A.nd) out[A.dcols[k0 + q]] = t;
     }
-    for (int j = threadIdx.x; j < n; j += NT) {
+    if (jt < n && r0 != -2) out[jt] = (r0 >= 0) ? cv0 * u[r0] : 0.0;
+    for (int j = jt + NT; j < n; j += NT) {
       const int r = A.colrow[j];
       if (r != -2) out[j] = (r >= 0) ? A.colval[j] * u[r] : 0.0;
     }
@@ -181,31 +214,43 @@ __device__ __forceinline__ void A_times2(const Matrix& A, const double* __restri
       g1[k] = ok ? u1[j] : 0.0;
       g2[k] = ok ? u2[j] : 0.0;
     }
-    __syncthreads();
-    for (int i0 = warp * 2; i0 < m; i0 += NWARP * 2) {
-      const bool two = i0 + 1 < m;
-      const double* __restrict__ ra = A.Ad + (size_t)i0 * ldd;
-      const double* __restrict__ rb = A.Ad + (size_t)(two ? i0 + 1 : i0) * ldd;
-      double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
-      for (int k = lane; k < ldd; k += 32) {
-        const double x = g1[k], q = g2[k], va = ra[k], vb = rb[k];
-        a0 += va * x;
-        a1 += va * q;
-        b0 += vb * x;
-        b1 += vb * q;
+    // singleton (slack) columns, one thread per row; the packed part is added below
+    for (int i = threadIdx.x; i < m; i += NT) {
+      double s1 = 0.0, s2 = 0.0;
+      for (int e = A.sing_ptr[i]; e < A.sing_ptr[i + 1]; e++) {
+        const double a = A.sing_a[e];
+        const int j = A.sing_col[e];
+        s1 += a * u1[j];
+        s2 += a * u2[j];
       }
-      warp_sum4(a0, a1, b0, b1);
-      if (lane < 2 && (lane == 0 || two)) {
-        const int i = i0 + lane;
-        double s1 = lane ? b0 : a0, s2 = lane ? b1 : a1;
-        for (int e = A.sing_ptr[i]; e < A.sing_ptr[i + 1]; e++) {
-          const double a = A.sing_a[e];
-          const int j = A.sing_col[e];
-          s1 += a * u1[j];
-          s2 += a * u2[j];
-        }
-        o1[i] = s1;
-        o2[i] = s2;
+      o1[i] = s1;
+      o2[i] = s2;
+    }
+    __syncthreads();
+    // four rows x two vectors per warp and pass: eight dot products, one 9-shuffle reduction
+    const int q = (lane >> 2) & 7;
+    for (int i0 = warp * 4; i0 < m; i0 += NWARP * 4) {
+      const double* __restrict__ r0 = A.Ad + (size_t)i0 * ldd;
+      const double* __restrict__ r1 = A.Ad + (size_t)min(i0 + 1, m - 1) * ldd;
+      const double* __restrict__ r2 = A.Ad + (size_t)min(i0 + 2, m - 1) * ldd;
+      const double* __restrict__ r3 = A.Ad + (size_t)min(i0 + 3, m - 1) * ldd;
+      double a[8];
+#pragma unroll
+      for (int c = 0; c < 8; c++) a[c] = 0.0;
+#pragma unroll 2
+      for (int k = lane; k < ldd; k += 32) {
+        const double x = g1[k], w = g2[k];
+        const double v0 = r0[k], v1 = r1[k], v2 = r2[k], v3 = r3[k];
+        a[0] += v0 * x; a[1] += v0 * w;
+        a[2] += v1 * x; a[3] += v1 * w;
+        a[4] += v2 * x; a[5] += v2 * w;
+        a[6] += v3 * x; a[7] += v3 * w;
+      }
+      const double t = warp_sum8(a, lane);
+      const int i = i0 + (q >> 1);
+      if ((lane & 3) == 0 && i < m) {
+        if (q & 1) o2[i] += t;
+        else o1[i] += t;
       }
     }
   } else {
@@ -377,64 +422,30 @@ static __device__ __forceinline__ void factor_ldl(int m, Work& W, double beta, d
 #include "ipm_syrk.cuh"
 namespace pb200 {
 
-// ---------------------------------------------------------------------------------------
-// S <- (L D)^-1 S ; S <- L^-T S ; dy += S      (ldl.cl:519-536), warp 0 only (v1, unused).
-// ---------------------------------------------------------------------------------------
-static __device__ __forceinline__ void tri_solve(int m, Work& W) {
-  if (threadIdx.x < 32) {
-    const int lane = threadIdx.x;
-    double* __restrict__ S = W.S;
-    const double* __restrict__ L = W.L;
-    const double* __restrict__ D = W.D;
-    for (int j = 0; j < m; j++) {
-      double dj = D[j];
-      double sj = S[j] / dj;
-      const double* col = L + cidx(j, j, m) - j;   // col[i] = L(i, j)
-      for (int i = j + 1 + lane; i < m; i += 32) S[i] -= sj * col[i] * dj;
-      __syncwarp();
-      if (lane == 0) S[j] = sj;
-    }
-    __syncwarp();
-    for (int j = m - 1; j >= 0; j--) {
-      const double* col = L + cidx(j, j, m) - j;
-      double acc = 0.0;
-      for (int i = j + 1 + lane; i < m; i += 32) acc += S[i] * col[i];
-      acc = warp_sum(acc);
-      if (lane == 0) {
-        double sj = S[j] - acc;
-        S[j] = sj;
-        W.dy[j] += sj;
-      }
-      __syncwarp();
-    }
-  }
-  __syncthreads();
-}
-
 // S = RHS - M dy ; returns max |S|   (ldl.cl:577-599); M is the block's full symmetric copy
-// in its L2-resident scratch slot, four rows per warp at a time.
+// in its L2-resident scratch slot, eight rows per warp at a time.
 static __device__ __forceinline__ double residual_M(int m, Work& W) {
   const int lane = threadIdx.x & 31, warp = warp_id();
+  const int q = (lane >> 2) & 7;
   double mx = 0.0;
-  for (int i0 = warp * 4; i0 < m; i0 += NWARP * 4) {
-    const double* __restrict__ r0 = W.M + (size_t)i0 * m;
-    const double* __restrict__ r1 = W.M + (size_t)min(i0 + 1, m - 1) * m;
-    const double* __restrict__ r2 = W.M + (size_t)min(i0 + 2, m - 1) * m;
-    const double* __restrict__ r3 = W.M + (size_t)min(i0 + 3, m - 1) * m;
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  for (int i0 = warp * 8; i0 < m; i0 += NWARP * 8) {
+    const double* __restrict__ r[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) r[c] = W.M + (size_t)min(i0 + c, m - 1) * m;
+    double a[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) a[c] = 0.0;
+#pragma unroll 2
     for (int j = lane; j < m; j += 32) {
       const double v = W.dy[j];
-      a0 += r0[j] * v;
-      a1 += r1[j] * v;
-      a2 += r2[j] * v;
-      a3 += r3[j] * v;
+#pragma unroll
+      for (int c = 0; c < 8; c++) a[c] += r[c][j] * v;
     }
-    warp_sum4(a0, a1, a2, a3);
-    if (lane < 4 && i0 + lane < m) {
-      const double acc = (lane == 0) ? a0 : (lane == 1) ? a1 : (lane == 2) ? a2 : a3;
-      const double r = W.RHS[i0 + lane] - acc;
-      W.S[i0 + lane] = r;
-      mx = fmax(mx, fabs(r));
+    const double t = warp_sum8(a, lane);
+    if ((lane & 3) == 0 && i0 + q < m) {
+      const double res = W.RHS[i0 + q] - t;
+      W.S[i0 + q] = res;
+      mx = fmax(mx, fabs(res));
     }
   }
   return block_max(mx, W.red);
@@ -513,7 +524,7 @@ static __device__ __forceinline__ void prepare_rhs(const Matrix& A, Work& W, dou
   }
   norms = sqrt(block_sum(ss, W.red));          // (syncs: t, d, q visible)
   // S <- A x ; RHS <- A q
-  A_times2(A, W.x, W.w, W.S, W.RHS, W.dg, W.g2);
+  A_times2(A, W.x, W.w, W.S, W.RHS, W.g1, W.g2);
   double rr = 0.0;
   for (int i = tid; i < m; i += NT) {
     double rho = W.b[i] - W.S[i];

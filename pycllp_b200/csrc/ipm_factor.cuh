@@ -538,11 +538,7 @@ static __device__ __forceinline__ bool factor_ldl_pipe(int m, Work& W, double be
       const long long tb = phase_begin(W);
       diag_block(m, j0, nb, W, delta, th, Wm, D1, rinv);
       phase_end(W, 9, tb);
-#ifndef PB200_EXPERIMENT_NO_OLD
     } else if (isK && more && j0 > 0) {
-#else
-    } else if (false) {
-#endif
       const long long tw = W.prof ? clock64() : 0;
       const double* PB = ((p + 1) & 1) ? PB1 : PB0;
       // units widx and widx+12 share their B fragments (two tiles per k-step), widx+24 alone;

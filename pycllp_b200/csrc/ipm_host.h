@@ -8,6 +8,7 @@
 namespace pb200 {
 
 size_t work_area_doubles(const Matrix& A);
+size_t vec_area_doubles(const Matrix& A);
 size_t smem_doubles(const Matrix& A, int L_in_smem, int vec_in_smem);
 cudaError_t launch_solve(const Matrix& A, const Batch& B, const Scratch& sc, const Params& p,
                          int grid, size_t smem_bytes, cudaStream_t stream);

@@ -15,23 +15,24 @@ static __device__ __forceinline__ void carve(const Matrix& A, const Scratch& sc,
   double* slot = sc.base + (size_t)blockIdx.x * sc.slot;
   size_t o = 0;
   W.red = smem + o; o += RED_SIZE;
-  size_t psz = (size_t)2 * m * NB + 512; // two panel-multiplier tables + split-K partials (ipm_factor.cuh)
-  if (psz < (size_t)SY_STAGES * SY_KC * A.sy_ldm) psz = (size_t)SY_STAGES * SY_KC * A.sy_ldm;
+  const size_t psz = work_area(A);
+  const size_t nw = w_doubles(A);
   double* v;
   if constexpr (VS) {
     W.P = smem + o; o += align16(psz);
-    W.dg = smem + o; o += align16(A.ldd > 0 ? A.ldd : 1);
     W.tiles = nullptr;
-    v = smem + o; o += align16((size_t)6 * n + 6 * m);
+    v = smem + o; o += align16((size_t)5 * n + nw + 6 * m);
+    W.dg = v + 5 * (size_t)n;   // = W.w (max(n, ldd) doubles): dead between prepare_rhs and step
   } else {   // large problems: only the reduction scratch and the SYRK macro tiles stay on-chip
     W.tiles = smem + o; o += 2 * TB * LDT;
     W.P = slot + sc.off_P;
     W.dg = slot + sc.off_dg;
     v = slot + sc.off_vec;
   }
-  W.g2 = W.P;      // second gather buffer of A_times2: the panel/stage area is idle then
+  W.g1 = W.P;      // gather buffers of A_times2: the panel/stage area is idle then
+  W.g2 = W.P + (A.ldd > 0 ? A.ldd : 1);
   W.x = v; W.z = v + n; W.c = v + 2 * n; W.t = v + 3 * n; W.d = v + 4 * n; W.w = v + 5 * n;
-  double* u = v + 6 * (size_t)n;
+  double* u = v + 5 * (size_t)n + nw;
   W.y = u; W.b = u + m; W.dy = u + 2 * m; W.S = u + 3 * m; W.RHS = u + 4 * m; W.D = u + 5 * m;
   if constexpr (LS) W.L = smem + o;
   else W.L = slot + sc.off_L;
@@ -162,7 +163,7 @@ size_t smem_doubles(const Matrix& A, int L_in_smem, int vec_in_smem) {
   auto al = [](size_t v) { return (v + 15) & ~(size_t)15; };
   size_t o = RED_SIZE;
   if (vec_in_smem) {
-    o += al(work_area_doubles(A)) + al(A.ldd > 0 ? A.ldd : 1) + al((size_t)6 * A.n + 6 * A.m);
+    o += al(work_area_doubles(A)) + al(vec_area_doubles(A));
   } else {
     o += 2 * TB * LDT;
   }
@@ -170,11 +171,8 @@ size_t smem_doubles(const Matrix& A, int L_in_smem, int vec_in_smem) {
   return o;
 }
 
-size_t work_area_doubles(const Matrix& A) {
-  size_t psz = (size_t)2 * A.m * NB + 512;
-  if (psz < (size_t)SY_STAGES * SY_KC * A.sy_ldm) psz = (size_t)SY_STAGES * SY_KC * A.sy_ldm;
-  return psz;
-}
+size_t work_area_doubles(const Matrix& A) { return work_area(A); }
+size_t vec_area_doubles(const Matrix& A) { return (size_t)5 * A.n + w_doubles(A) + 6 * A.m; }
 
 typedef void (*solve_kernel_t)(Matrix, Batch, Scratch, Params);
 static solve_kernel_t pick_kernel(int L_in_smem, int vec_in_smem) {

@@ -4,8 +4,8 @@
 // diagonal afterwards).  The packed operand lives in global memory pre-tiled exactly as it
 // is used: chunk ch = SY_KC consecutive packed columns, stored k-major with the m rows padded
 // to SY ldm (ldm = 4 mod 16 makes every DMMA fragment load bank-conflict free), so one
-// cp.async.bulk (TMA, 1-D) brings a whole chunk into shared memory; two stages, one
-// mbarrier each.  The lower triangle of M is cut into 8x8 tiles; a warp owns up to SY_SEG
+// cp.async.bulk (TMA, 1-D) brings a whole chunk into shared memory; SY_STAGES stages, one
+// mbarrier each; the last warp to finish a stage refills it.  The lower triangle of M is cut into 8x8 tiles; a warp owns up to SY_SEG
 // "segments" per pass (one tile row x up to SY_CW consecutive tile columns) and keeps their
 // accumulators in registers for the whole K loop, so every A fragment is loaded once per
 // SY_CW DMMAs and the row fragment is the one scaled by d (one DMUL per segment).  The
@@ -15,7 +15,7 @@
 
 namespace pb200 {
 
-constexpr int RED_MBAR = 216;   // 2 x SY_STAGES 8-byte mbarriers inside W.red (216..223)
+constexpr int RED_MBAR = 216;   // SY_STAGES 8-byte mbarriers + SY_STAGES int counters inside W.red (216..223)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -46,8 +46,12 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
       : "memory");
 }
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+// shared-memory counter: release this thread's (warp's, after __syncwarp) earlier accesses,
+// acquire those of the threads that incremented before
+__device__ __forceinline__ int atom_add_acq_rel(int* p, int v) {
+  int old;
+  asm volatile("atom.acq_rel.cta.shared::cta.add.s32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
+  return old;
 }
 
 static __device__ __forceinline__ void form_M_dense_tma(const Matrix& A, Work& W) {
@@ -59,12 +63,14 @@ static __device__ __forceinline__ void form_M_dense_tma(const Matrix& A, Work& W
   const uint32_t chunk_bytes = (uint32_t)(SY_KC * ldm * sizeof(double));
   const int stage_doubles = SY_KC * ldm;
   uint64_t* full = reinterpret_cast<uint64_t*>(W.red + RED_MBAR);
-  uint64_t* empty = full + SY_STAGES;
+  // done[s]: warps that have finished with the chunk in stage s.  The LAST warp to finish
+  // refills the stage, so no warp ever waits for the others to release a stage.
+  int* done = reinterpret_cast<int*>(full + SY_STAGES);
 
   for (int k = tid; k < A.ldd; k += NT) W.dg[k] = (k < A.nd) ? W.d[A.dcols[k]] : 0.0;
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < SY_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], NWARP); }
+    for (int s = 0; s < SY_STAGES; s++) { mbar_init(&full[s], 1); done[s] = 0; }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -72,7 +78,7 @@ static __device__ __forceinline__ void form_M_dense_tma(const Matrix& A, Work& W
   if (tid == 0) {
     // the staging area was last touched through the generic proxy (the factorisation's P)
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    for (int c = 0; c < SY_STAGES - 1 && c < total; c++) {
+    for (int c = 0; c < SY_STAGES && c < total; c++) {
       mbar_expect_tx(&full[c], chunk_bytes);
       tma_load_1d(W.P + c * stage_doubles, A.sy_A + (size_t)(c % nch) * stage_doubles, chunk_bytes, &full[c]);
     }
@@ -97,20 +103,7 @@ static __device__ __forceinline__ void form_M_dense_tma(const Matrix& A, Work& W
 
     for (int ch = 0; ch < nch; ch++, gch++) {
       const int st = gch % SY_STAGES;
-      if (tid == 0) {
-        // keep SY_STAGES-1 chunks in flight: refill the stage that chunk gch-1 occupied
-        const int c = gch + SY_STAGES - 1;
-        if (c < total) {
-          const int cs = c % SY_STAGES;
-          if (c >= SY_STAGES) mbar_wait(&empty[cs], ((c / SY_STAGES) - 1) & 1);
-          mbar_expect_tx(&full[cs], chunk_bytes);
-          tma_load_1d(W.P + cs * stage_doubles, A.sy_A + (size_t)(c % nch) * stage_doubles,
-                      chunk_bytes, &full[cs]);
-        }
-      }
-#ifndef PB200_EXPERIMENT_NOWAIT
       mbar_wait(&full[st], (gch / SY_STAGES) & 1);
-#endif
       const double* __restrict__ S = W.P + st * stage_doubles;
 #pragma unroll
       for (int ks = 0; ks < SY_KC / 4; ks++) {
@@ -131,7 +124,17 @@ static __device__ __forceinline__ void form_M_dense_tma(const Matrix& A, Work& W
         }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[st]);        // this warp is done with stage st
+      if (lane == 0) {                               // this warp is done with stage st
+        if (atom_add_acq_rel(&done[st], 1) == NWARP - 1) {
+          done[st] = 0;
+          const int c = gch + SY_STAGES;
+          if (c < total) {
+            mbar_expect_tx(&full[st], chunk_bytes);
+            tma_load_1d(W.P + st * stage_doubles, A.sy_A + (size_t)(c % nch) * stage_doubles,
+                        chunk_bytes, &full[st]);
+          }
+        }
+      }
     }
     phase_end(W, 14, tk);
     tk = phase_begin(W);

@@ -12,7 +12,7 @@ constexpr int TB = 64;           // SYRK macro tile (TB x TB outputs per pass)
 constexpr int KC = 16;           // SYRK k-chunk staged in shared memory
 constexpr int LDT = KC + 4;      // padded leading dimension of a staged tile (conflict-free)
 constexpr int SY_KC = 8;         // TMA-staged SYRK: packed columns per chunk
-constexpr int SY_STAGES = 2;     //   chunks in flight (ring of shared-memory stages)
+constexpr int SY_STAGES = 3;     //   chunks in flight (ring of shared-memory stages)
 constexpr int SY_SEG = 3;        //   segments per warp per pass
 constexpr int SY_CW = 4;         //   8x8 tiles per segment
 
@@ -55,6 +55,25 @@ struct Matrix {
   const int *me_ptr, *me_i, *me_j, *mt_k;
   const double* mt_w;
 };
+
+// doubles of the shared work area W.P: two panel-multiplier tables + split-K partials
+// (ipm_factor.cuh), the TMA stages of the SYRK, or the two gather buffers of A_times2
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+inline size_t work_area(const Matrix& A) {
+  size_t psz = (size_t)2 * A.m * NB + 512;
+  const size_t st = (size_t)SY_STAGES * SY_KC * A.sy_ldm;
+  const size_t g = (size_t)2 * (A.ldd > 0 ? A.ldd : 1);
+  if (psz < st) psz = st;
+  if (psz < g) psz = g;
+  return psz;
+}
+// doubles of the vector W.w, which also serves as the gather of d on the packed SYRK columns
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+inline size_t w_doubles(const Matrix& A) { return (size_t)(A.ldd > A.n ? A.ldd : A.n); }
 
 struct Batch {
   int N;
