@@ -12,6 +12,7 @@
 // result goes straight into the factorisation's packed storage W.L and (both triangles)
 // into W.M for the residual.
 #pragma once
+#include <type_traits>
 
 namespace pb200 {
 
@@ -52,6 +53,54 @@ __device__ __forceinline__ int atom_add_acq_rel(int* p, int v) {
   int old;
   asm volatile("atom.acq_rel.cta.shared::cta.add.s32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
   return old;
+}
+
+// The DMMAs of one staged chunk for one warp.  Measured on B200 (tools/syrk_loop_probe.cu): a
+// PREDICATED-OFF DMMA still occupies the FP64 tensor pipe for its full 16 cycles, so the tile
+// counts must be compile-time or branched on, never predicated.  N2 >= 0: segments 0 and 1
+// hold SY_CW tiles each and segment 2 holds N2 (the shape the host-side balancer produces
+// for all but tiny problems) -> straight-line code.  N2 < 0: any shape; full segments take
+// an unpredicated path, partial ones a predicated one.
+template <int N2>
+__device__ __forceinline__ void syrk_chunk(double (&acc)[SY_SEG][SY_CW][2], const double* __restrict__ S,
+                                           const double* __restrict__ dgc, int ldm, int g, int tg,
+                                           const int (&segI)[SY_SEG], const int (&segJ)[SY_SEG],
+                                           const int (&segN)[SY_SEG]) {
+#pragma unroll
+  for (int ks = 0; ks < SY_KC / 4; ks++) {
+    const double dk = dgc[ks * 4 + tg];
+    const double* __restrict__ col = S + (ks * 4 + tg) * ldm + g;
+    if constexpr (N2 >= 0) {
+      double as[SY_SEG];
+#pragma unroll
+      for (int s = 0; s < SY_SEG; s++) as[s] = col[8 * segI[s]] * dk;   // (empty segment: tile 0)
+#pragma unroll
+      for (int s = 0; s < SY_SEG; s++) {
+#pragma unroll
+        for (int t = 0; t < SY_CW; t++) {
+          if (s < SY_SEG - 1 || t < N2) {
+            const double b = col[8 * (segJ[s] + t)];
+            dmma884(acc[s][t][0], acc[s][t][1], as[s], b);
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int s = 0; s < SY_SEG; s++) {
+        if (segN[s] == SY_CW) {
+          const double as = col[8 * segI[s]] * dk;
+#pragma unroll
+          for (int t = 0; t < SY_CW; t++) dmma884(acc[s][t][0], acc[s][t][1], as, col[8 * (segJ[s] + t)]);
+        } else if (segN[s] > 0) {
+          const double as = col[8 * segI[s]] * dk;
+#pragma unroll
+          for (int t = 0; t < SY_CW; t++) {
+            if (t < segN[s]) dmma884(acc[s][t][0], acc[s][t][1], as, col[8 * (segJ[s] + t)]);
+          }
+        }
+      }
+    }
+  }
 }
 
 static __device__ __forceinline__ void form_M_dense_tma(const Matrix& A, Work& W) {
@@ -101,41 +150,34 @@ static __device__ __forceinline__ void form_M_dense_tma(const Matrix& A, Work& W
 #pragma unroll
       for (int t = 0; t < SY_CW; t++) acc[s][t][0] = acc[s][t][1] = 0.0;
 
-    for (int ch = 0; ch < nch; ch++, gch++) {
-      const int st = gch % SY_STAGES;
-      mbar_wait(&full[st], (gch / SY_STAGES) & 1);
-      const double* __restrict__ S = W.P + st * stage_doubles;
-#pragma unroll
-      for (int ks = 0; ks < SY_KC / 4; ks++) {
-        const double dk = W.dg[ch * SY_KC + ks * 4 + tg];
-        const double* __restrict__ col = S + (ks * 4 + tg) * ldm + g;
-#pragma unroll
-        for (int s = 0; s < SY_SEG; s++) {
-          if (segN[s] > 0) {
-            const double as = col[8 * segI[s]] * dk;
-#pragma unroll
-            for (int t = 0; t < SY_CW; t++) {
-              if (t < segN[s]) {
-                const double b = col[8 * (segJ[s] + t)];
-                dmma884(acc[s][t][0], acc[s][t][1], as, b);
-              }
+    // the chunk loop, instantiated for the shape of this warp's segments
+    auto chunk_loop = [&](auto n2c) {
+      constexpr int N2 = decltype(n2c)::value;
+      for (int ch = 0; ch < nch; ch++, gch++) {
+        const int st = gch % SY_STAGES;
+        mbar_wait(&full[st], (gch / SY_STAGES) & 1);
+        syrk_chunk<N2>(acc, W.P + st * stage_doubles, W.dg + ch * SY_KC, ldm, g, tg, segI, segJ, segN);
+        __syncwarp();
+        if (lane == 0) {                               // this warp is done with stage st
+          if (atom_add_acq_rel(&done[st], 1) == NWARP - 1) {
+            done[st] = 0;
+            const int c = gch + SY_STAGES;
+            if (c < total) {
+              mbar_expect_tx(&full[st], chunk_bytes);
+              tma_load_1d(W.P + st * stage_doubles, A.sy_A + (size_t)(c % nch) * stage_doubles,
+                          chunk_bytes, &full[st]);
             }
           }
         }
       }
-      __syncwarp();
-      if (lane == 0) {                               // this warp is done with stage st
-        if (atom_add_acq_rel(&done[st], 1) == NWARP - 1) {
-          done[st] = 0;
-          const int c = gch + SY_STAGES;
-          if (c < total) {
-            mbar_expect_tx(&full[st], chunk_bytes);
-            tma_load_1d(W.P + st * stage_doubles, A.sy_A + (size_t)(c % nch) * stage_doubles,
-                        chunk_bytes, &full[st]);
-          }
-        }
-      }
-    }
+    };
+    const bool regular = (segN[0] == SY_CW) && (segN[1] == SY_CW);
+    if (!regular) chunk_loop(std::integral_constant<int, -1>{});
+    else if (segN[2] == 0) chunk_loop(std::integral_constant<int, 0>{});
+    else if (segN[2] == 1) chunk_loop(std::integral_constant<int, 1>{});
+    else if (segN[2] == 2) chunk_loop(std::integral_constant<int, 2>{});
+    else if (segN[2] == 3) chunk_loop(std::integral_constant<int, 3>{});
+    else chunk_loop(std::integral_constant<int, 4>{});
     phase_end(W, 14, tk);
     tk = phase_begin(W);
     // epilogue: tiles -> packed L storage and full M

@@ -56,6 +56,14 @@ int main() {
   RUN(1, "V1 LDS a, LDS b, DMMA (no DMUL)");
   RUN(2, "V2 register operands only");
   RUN(3, "V3 = V0 + runtime segment predicates");
+#define RUNN(a, b, c, name) probe<3><<<148, 512, smem>>>(out, cyc, iters, ldm, a, b, c); cudaDeviceSynchronize(); \
+  probe<3><<<148, 512, smem>>>(out, cyc, iters, ldm, a, b, c); cudaDeviceSynchronize(); \
+  cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost); \
+  printf("%-46s %7.1f cyc per k-step (%d DMMA/warp; DMMA-bound = %d)\n", name, (double)h / iters, a + b + c, 64 * (a + b + c));
+  RUNN(4, 4, 2, "V3 segments 4,4,2 (2 predicated-off DMMAs)");
+  RUNN(4, 4, 0, "V3 segments 4,4,0 (third segment branched over)");
+  RUNN(4, 2, 2, "V3 segments 4,2,2 (4 predicated-off DMMAs)");
+  RUNN(2, 2, 2, "V3 segments 2,2,2 (6 predicated-off DMMAs)");
   printf("%s\n", cudaGetErrorString(cudaGetLastError()));
   return 0;
 }
