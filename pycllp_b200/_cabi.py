@@ -203,7 +203,7 @@ class Engine(object):
         out = (ctypes.c_ulonglong * 16)()
         self._check(self._lib.pycllp_b200_phase_profile(self._h, int(enable), out), "phase_profile")
         names = ("rhs_norms", "form_M", "factor", "tri_solve", "residual", "step",
-                 "f_copy", "syrk_w1", "f_stepA", "f_stepB", "f_stepC", "f_stepD", "syrk_wait", "f_bulk_w1", "syrk_kloop", "syrk_epilogue")
+                 "f_copy", "f_waitEd", "f_blockrow", "f_diag", "f_solve", "f_table", "f_waitE3", "f_old", "f_waitEb", "f_update")
         return {k: int(out[i]) for i, k in enumerate(names)}
 
     # -- introspection ---------------------------------------------------------------------

@@ -107,7 +107,7 @@ int finish_setup(pycllp_b200_engine* e, int max_problems) {
   if (smem_doubles(e->A, Ls, Vs) * 8 > limit)
     return fail(e, PYCLLP_B200_ERR_ARG, "problem too large for the shared-memory work area");
   e->smem_bytes = smem_doubles(e->A, Ls, Vs) * 8;
-  const size_t lsz = (size_t)m * (m + 1) / 2;
+  const size_t lsz = packed_doubles(m);
   size_t slot = al16((size_t)m * m);
   e->sc.off_L = slot;
   if (!Ls) slot += al16(lsz);
@@ -467,7 +467,7 @@ int pycllp_b200_ldl(pycllp_b200_engine* e, int N, int m, const double* AA, doubl
   if (N <= 0 || m <= 0 || !AA || !L || !D) return fail(e, PYCLLP_B200_ERR_ARG, "ldl: bad argument");
   DeviceGuard guard(e->device);
   const size_t lsz = (size_t)m * (m + 1) / 2;
-  const size_t slot = al16((size_t)2 * m * NB + 512 + lsz + m);
+  const size_t slot = al16((size_t)2 * m * NB + 512 + packed_doubles(m) + m);
   const int grid = std::min(N, e->num_sms);
   double *d_AA = nullptr, *d_L = nullptr, *d_D = nullptr, *d_s = nullptr;
   cudaError_t err = cudaMalloc(&d_AA, (size_t)N * m * m * sizeof(double));

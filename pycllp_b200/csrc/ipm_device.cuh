@@ -71,9 +71,9 @@ __device__ __forceinline__ double block_max(double v, double* red) {
 
 // packed lower triangle, COLUMN-major: column j holds rows j..m-1 contiguously, so that a
 // "thread per row" sweep over a column is a unit-stride access.
-__device__ __forceinline__ size_t cidx(int i, int j, int m) {
-  return (size_t)j * m - (size_t)j * (j - 1) / 2 + (i - j);
-}
+// (valid while the packed size fits 31 bits; layout: packed_off in ipm_types.h)
+__device__ __forceinline__ int coff(int j, int m) { return packed_off(j, m); }
+__device__ __forceinline__ int cidx(int i, int j, int m) { return packed_off(j, m) + i; }
 
 // D(8x8) += A(8x4) * B(4x8), FP64 tensor core (DMMA).
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
@@ -84,7 +84,8 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 
 // Per-block working set (pointers into shared memory or the block's scratch slot).
 struct Work {
-  double *x, *z, *c, *t, *d, *w;        // n each
+  double *x, *z, *t, *d, *w;            // n each
+  const double* c;                      // n: this problem's objective, read from the batch in global memory
   double *y, *b, *dy, *S, *RHS, *D;     // m each
   double* P;                            // max(m*NB, 2*TB*LDT): panel multipliers / SYRK tiles
   double* dg;                           // ldd : d gathered on the packed SYRK columns
@@ -106,11 +107,11 @@ constexpr int RED_PROF = 224;
 __device__ __forceinline__ long long phase_begin(const Work& W) {
   return W.prof ? clock64() : 0;
 }
-__device__ __forceinline__ void phase_end(const Work& W, int id, long long t0) {
+__device__ __forceinline__ void phase_end(const Work& W, int id, long long t0, int who = 0) {
   if (W.prof) {
     const unsigned long long dt = (unsigned long long)(clock64() - t0);
     unsigned long long* slot = reinterpret_cast<unsigned long long*>(W.red + RED_PROF) + id;
-    if (threadIdx.x == 0) *slot += dt;
+    if (threadIdx.x == who) *slot += dt;
   }
 }
 
@@ -476,7 +477,12 @@ static __device__ __forceinline__ void solve_normal(const Matrix& A, Work& W, co
   __syncthreads();
   phase_end(W, 6, t0);
   bool redo = true;
+  #ifdef PB200_FACTOR_PIPE
   if (LS && m <= 8 * 35) redo = factor_ldl_pipe(m, W, beta, p.ldl_delta, W.RHS, W.S);
+#else
+  if (LS && m <= 208) redo = factor_ldl_ahead(m, W, beta, p.ldl_delta, W.RHS, W.S);
+  else if (LS && m <= 8 * 35) redo = factor_ldl_pipe(m, W, beta, p.ldl_delta, W.RHS, W.S);
+#endif
   if (redo) {
     if (LS && m <= 8 * 35) {     // speculation failed somewhere: restore M and take the exact-capable path
       for (int e = tid; e < m * m; e += NT) {
@@ -514,7 +520,7 @@ static __device__ __forceinline__ void prepare_rhs(const Matrix& A, Work& W, dou
   At_times(A, W.y, W.w);
   double ss = 0.0;
   for (int j = tid; j < n; j += NT) {
-    double v = W.w[j], xj = W.x[j], zj = W.z[j], cj = W.c[j];
+    double v = W.w[j], xj = W.x[j], zj = W.z[j], cj = W.c[j];   // (c: straight from the batch)
     double sig = cj - v + zj;
     ss += sig * sig;
     double tj = cj - v + mu / xj;

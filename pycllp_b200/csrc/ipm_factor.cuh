@@ -65,8 +65,6 @@ static __device__ __forceinline__ void panel_exact(int m, int j0, int nb, Work& 
   }
 }
 
-// 32-bit packed index: L(i, j) lives at coff(j, m) + i   (valid while m(m+1)/2 < 2^31)
-__device__ __forceinline__ int coff(int j, int m) { return j * (m - 1) - ((j * (j - 1)) >> 1); }
 
 // approximate single-precision reciprocal (one MUFU), seed of rcp_pos
 __device__ __forceinline__ float rcp_approx_f32(float x) {
@@ -199,7 +197,7 @@ __device__ __forceinline__ void panel_update_tiles(const double* __restrict__ L,
   c0 = c1 = u0 = u1 = 0.0;
   if (j0 == 0) return;
   const double* pa = L + coff(tg, m) + ra;      // column k = tg, row ra
-  int d = 4 * m - 10 - 4 * tg;                  // coff(k + 4) - coff(k); decreases by 16 per step
+  int d = 4 * m - 8 - 4 * tg;                   // coff(k + 4) - coff(k); decreases by 16 per step
   const double* pb = P + tg * NB + g;
   double a1, a2, a3 = 0.0, a4 = 0.0, b1, b2;
   a1 = pa[0]; if (TWO) a3 = pa[drow]; pa += d; d -= 16;
@@ -461,7 +459,7 @@ __device__ __forceinline__ void pipe_old_unit(const double* __restrict__ L, cons
   const int nks = K >> 2;
   int k = tg;
   const double* pa = L + coff(k, m) + rs;
-  int d = 4 * m - 10 - 4 * tg;
+  int d = 4 * m - 8 - 4 * tg;
   const double* pb = PB + tg * NB + g;
   int ks = 0;
   for (; ks + 4 <= nks; ks += 4) {
@@ -687,6 +685,350 @@ static __device__ __forceinline__ bool factor_ldl_pipe(int m, Work& W, double be
     phase_end(W, 11, tq);
   }
   return bad;
+}
+
+// ---------------------------------------------------------------------------------------
+// factor_ldl_ahead: the same factorisation with the SERIAL CHAIN ON ITS OWN WARP.
+//
+// The chain  diag_block(p) -> rows of block p+1 solved against it -> diagonal tile p+1 updated
+// -> diag_block(p+1)  is the critical path of any LDL' (one warp, ~3k cycles per panel).  Here
+// warp 0 runs nothing but that chain, one panel AHEAD of the other fifteen warps, and the two
+// sides meet only at two named barriers per panel:
+//   warp 0, panel p :  diag_block(p) ; [E3: others finished panel p-1] ; block_row(p) (rows
+//                      j1..j1+7 of panel p, gives W' = D L(block p+1, panel p)) ; tile (p+1,p+1)
+//                      -= L(block p+1, panel p) W'^T ; [E1: arrive]
+//   others, panel p :  [E1] ; step 1, one thread per row i >= j1+8 (and the rhs row): solve the
+//                      row against block p, then subtract its product with W' from panel p+1 ;
+//                      [O1] theta check ; step 2: multiplier table D_k L(rows of block p+2, k),
+//                      k < j1 ; [O2] ; step 3: panel p+2 -= L(:, k<j1) table^T on the FP64 tensor
+//                      cores (twelve warps of sub-partitions 1-3, warp 0 keeps sub-partition 0
+//                      free of DMMAs, see profiles/fp64_latency_r01.txt) ; [E3: arrive]
+// so every panel q receives the columns k < 8(q-1) two panels early (step 3 of panel q-2) and
+// the eight columns of panel q-1 one panel early (step 1 of panel q-1 / warp 0).
+// The right-hand side rides along as an extra row kept in Sf (in place).  Speculative like
+// factor_ldl_pipe: returns true if some panel could not be proven equivalent to the sequential
+// rule (theta clamp active, huge or tied pivot); the caller then redoes the factorisation.
+// Requires L in shared memory and m <= 8*35.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void nbar_sync(int id, int nthreads) {
+  asm volatile("barrier.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void nbar_arrive(int id, int nthreads) {
+  asm volatile("barrier.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// named barriers; the three warp 0 <-> others events are double-buffered by panel parity so
+// that an early arrival for panel p+1 can never be counted into the phase of panel p
+constexpr int BAR_ED = 1, BAR_EB = 3, BAR_E3 = 5, BAR_O1 = 7, BAR_O2 = 8;
+
+// warp 0: rows j1..j1+7 of panel j0 against the eliminated block (Wm, rinv); outputs the
+// scaled rows to L storage and Lb[8][8], the unscaled ones (D_k l_k) to Wp[8][8]; then the
+// diagonal tile of panel j1 -= Lb Wp^T (two DMMAs).
+static __device__ __forceinline__ void block_row(int m, int j0, int nb, Work& W, const double* Wm,
+                                                 const double* rinv, int* th, double* Wp, double* Lb) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
+  double* __restrict__ L = W.L;
+  const int j1 = j0 + 8;
+  const int row = j1 + lane;
+  const bool valid = lane < 8 && row < m;
+  const int rs = valid ? row : j0;           // (always a valid address)
+  double c[8], un[8];
+  int hm[8];
+#pragma unroll
+  for (int jj = 0; jj < 8; jj++) {
+    const double v = L[coff(min(j0 + jj, m - 1), m) + rs];
+    c[jj] = (valid && jj < nb) ? v : 0.0;
+  }
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    hm[k] = dbl_hi(c[k]) & 0x7fffffff;
+    un[k] = c[k];
+    const double lk = c[k] * rinv[k];
+#pragma unroll
+    for (int jj = k + 1; jj < 8; jj++) c[jj] -= lk * Wm[jj * 8 + k];
+    c[k] = lk;
+  }
+  if (lane < 8) {
+#pragma unroll
+    for (int jj = 0; jj < 8; jj++) {
+      Wp[lane * 8 + jj] = un[jj];
+      Lb[lane * 8 + jj] = c[jj];
+      if (valid && jj < nb) L[coff(j0 + jj, m) + row] = c[jj];
+    }
+  }
+  {
+    int mine = 0;
+#pragma unroll
+    for (int jj = 0; jj < 8; jj++) {
+      const int r = __reduce_max_sync(0xffffffffu, hm[jj]);
+      if (lane == jj) mine = r;
+    }
+    if (lane < 8) th[lane] = max(th[lane], mine);      // only warp 0 touches th before E1
+  }
+  __syncwarp();
+  if (j1 < m) {
+    double c0 = 0.0, c1 = 0.0;
+    dmma884(c0, c1, Lb[g * 8 + tg], Wp[g * 8 + tg]);
+    dmma884(c0, c1, Lb[g * 8 + 4 + tg], Wp[g * 8 + 4 + tg]);
+    const int r2 = j1 + g;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int col = 2 * tg + h;
+      if (r2 < m && col <= g) L[coff(j1 + col, m) + r2] -= (h ? c1 : c0);
+    }
+  }
+  __syncwarp();
+}
+
+// Step 3 of factor_ldl_ahead for one warp: a unit of SIXTEEN rows ra..ra+15 against the
+// multiplier table (row stride PBS = 12: the four k-rows of a B fragment fall into disjoint
+// banks).  One 16-byte load per lane brings rows ra+2g and ra+2g+1 of column k -- two
+// interleaved 8-row tiles (even rows / odd rows) -- and every column is a run of sixteen
+// consecutive doubles, i.e. exactly one conflict-free wavefront (the packed layout keeps
+// column starts even).  Two split-K chains per tile; operands of the next step are loaded
+// before the DMMAs of the current one.  K = 8, 16, ...  Rows past the end of a column read
+// whatever follows (finite or not, a DMMA row only feeds the same row of the result, which
+// is then not stored).
+constexpr int PBS = 12;
+__device__ __forceinline__ void old_update16(const double* __restrict__ L, const double* __restrict__ PB,
+                                             int m, int K, int tg, int g, int ra, double& c0, double& c1,
+                                             double& u0, double& u1) {
+  double e0 = 0.0, e1 = 0.0, v0 = 0.0, v1 = 0.0;
+  c0 = c1 = u0 = u1 = 0.0;
+  const double* pa = L + coff(tg, m) + ra + 2 * g;
+  int d = 4 * m - 8 - 4 * tg;                   // coff(k + 4) - coff(k); decreases by 16 per step
+  const double* pb = PB + tg * PBS + g;
+  double2 a1 = *reinterpret_cast<const double2*>(pa); pa += d; d -= 16;
+  double2 a2 = *reinterpret_cast<const double2*>(pa); pa += d; d -= 16;
+  double b1 = pb[0], b2 = pb[4 * PBS]; pb += 8 * PBS;
+  for (int k0 = 8; k0 < K; k0 += 8) {
+    const double2 n1 = *reinterpret_cast<const double2*>(pa); pa += d; d -= 16;
+    const double2 n2 = *reinterpret_cast<const double2*>(pa); pa += d; d -= 16;
+    const double m1 = pb[0], m2 = pb[4 * PBS]; pb += 8 * PBS;
+    dmma884(c0, c1, a1.x, b1);
+    dmma884(u0, u1, a1.y, b1);
+    dmma884(e0, e1, a2.x, b2);
+    dmma884(v0, v1, a2.y, b2);
+    a1 = n1; a2 = n2; b1 = m1; b2 = m2;
+  }
+  dmma884(c0, c1, a1.x, b1);
+  dmma884(u0, u1, a1.y, b1);
+  dmma884(e0, e1, a2.x, b2);
+  dmma884(v0, v1, a2.y, b2);
+  c0 += e0; c1 += e1; u0 += v0; u1 += v1;
+}
+
+// Step 1 of factor_ldl_ahead for one row, two threads per row.  Part a: solve the row
+// against the eliminated block (both threads, thread `half == 0` stores); part b: subtract
+// the row's product with W' from four of the eight columns of the next panel.
+template <bool FULL>
+__device__ __forceinline__ void step1_solve(double* __restrict__ L, int m, int j0, int nb, int row, int half,
+                                            const double* __restrict__ Wm, const double* __restrict__ rinv,
+                                            double (&c)[8], int (&hmax)[8]) {
+#pragma unroll
+  for (int jj = 0; jj < 8; jj++) c[jj] = (FULL || jj < nb) ? L[coff(min(j0 + jj, m - 1), m) + row] : 0.0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    hmax[k] = max(hmax[k], dbl_hi(c[k]) & 0x7fffffff);
+    const double lk = c[k] * rinv[k];
+#pragma unroll
+    for (int jj = k + 1; jj < 8; jj++) c[jj] -= lk * Wm[jj * 8 + k];
+    c[k] = lk;
+  }
+  if (half == 0) {
+#pragma unroll
+    for (int jj = 0; jj < 8; jj++)
+      if (FULL || jj < nb) L[coff(min(j0 + jj, m - 1), m) + row] = c[jj];
+  }
+}
+template <bool FULL>
+__device__ __forceinline__ void step1_update(double* __restrict__ L, int m, int j1, int row, int half,
+                                             const double* __restrict__ Wp, const double (&c)[8]) {
+  const int nb1 = min(NB, m - j1);
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const int jj = 4 * half + q;
+    const double2* __restrict__ w2 = reinterpret_cast<const double2*>(Wp + jj * 8);
+    const double2 w01 = w2[0], w23 = w2[1], w45 = w2[2], w67 = w2[3];
+    const double s = ((c[0] * w01.x + c[1] * w01.y) + (c[2] * w23.x + c[3] * w23.y)) +
+                     ((c[4] * w45.x + c[5] * w45.y) + (c[6] * w67.x + c[7] * w67.y));
+    if (FULL || jj < nb1) L[coff(min(j1 + jj, m - 1), m) + row] -= s;
+  }
+}
+
+static __device__ __forceinline__ bool factor_ldl_ahead(int m, Work& W, double beta, double delta,
+                                                        const double* __restrict__ rhs,
+                                                        double* __restrict__ Sf) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = warp_id();
+  const int g = lane >> 2, tg = lane & 3;
+  double* __restrict__ L = W.L;
+  double* __restrict__ D = W.D;
+  double* PB = W.P;                                   // multiplier table [k][8]
+  double* xtra = W.P + (size_t)2 * m * NB;            // 512 spare doubles of the work area
+  // per-parity block data at xtra + 80 par: Wm[64], D1[8], rinv[8]
+  double* Wp = xtra + 160;                            // D_k L(block p+1, panel p)   [8][8]
+  double* Lb = xtra + 224;                            // L(block p+1, panel p)       [8][8]
+  int* thbuf = reinterpret_cast<int*>(W.red + RED_TH);
+  const double inv_beta2 = 1.0 / (beta * beta);
+  const int np = (m + 7) >> 3;
+  const int wsub = warp & 3;
+  const bool isK = wsub != 0;
+  const int widx = (warp >> 2) * 3 + wsub - 1;        // 0..11 for the DMMA warps
+  const int NOTH = NT - 32;                           // threads other than warp 0
+  bool bad = false;
+
+  for (int i = tid; i < m; i += NT) Sf[i] = rhs[i];
+  if (tid < 16) thbuf[tid] = 0;
+  __syncthreads();
+
+  if (warp == 0) {
+    // ------------------------------ the serial chain ------------------------------
+    for (int p = 0; p < np; p++) {
+      const int j0 = 8 * p, nb = min(NB, m - j0), par = p & 1;
+      int* th = thbuf + par * 8;
+      double* blk = xtra + 80 * par;
+      const long long tb = phase_begin(W);
+      diag_block(m, j0, nb, W, delta, th, blk, blk + 64, blk + 72);
+      __syncwarp();
+      if (lane < nb) D[j0 + lane] = blk[64 + lane];
+      nbar_arrive(BAR_ED + par, NT);                  // block p eliminated
+      phase_end(W, 9, tb);
+      const long long tw = phase_begin(W);
+      if (p > 0) nbar_sync(BAR_E3 + (par ^ 1), NT);   // others are done with panel p-1
+      phase_end(W, 12, tw);
+      const long long tr = phase_begin(W);
+      if (j0 + 8 < m) block_row(m, j0, nb, W, blk, blk + 72, th, Wp, Lb);
+      nbar_arrive(BAR_EB + par, NT);                  // W' of panel p published
+      phase_end(W, 8, tr);
+    }
+  } else {
+    // ------------------------------ everything else -------------------------------
+    const int t = widx * 32 + lane;                   // slot of the DMMA warps' threads
+    const int r = t >> 1, half = t & 1;               // step 1: two threads per row
+    for (int p = 0; p < np; p++) {
+      const int j0 = 8 * p, j1 = j0 + 8, j2 = j0 + 16;
+      const int nb = min(NB, m - j0), par = p & 1;
+      const double* blk = xtra + 80 * par;
+      const double* Wm = blk;
+      const double* rinv = blk + 72;
+      int* th = thbuf + par * 8;
+      const int nrows = max(0, m - j1 - 8);
+      const bool has1 = j1 < m;
+      const bool full = (nb == NB) && (!has1 || m - j1 >= NB);
+      long long tq = phase_begin(W);
+      nbar_sync(BAR_ED + par, NT);
+      phase_end(W, 7, tq, 32);
+      tq = phase_begin(W);
+      // ---- step 1a: solve the rows below block p+1 against block p; rhs row on warp 4 ----
+      double c[8];
+      if (isK) {
+        int hmax[8];
+#pragma unroll
+        for (int jj = 0; jj < 8; jj++) hmax[jj] = 0;
+        if (r < nrows) {
+          if (full) step1_solve<true>(L, m, j0, nb, j1 + 8 + r, half, Wm, rinv, c, hmax);
+          else step1_solve<false>(L, m, j0, nb, j1 + 8 + r, half, Wm, rinv, c, hmax);
+        }
+        int hm = 0;
+#pragma unroll
+        for (int jj = 0; jj < 8; jj++) {
+          const int rr = __reduce_max_sync(0xffffffffu, hmax[jj]);
+          if (lane == jj) hm = rr;
+        }
+        if (lane < 8 && hm > 0) atomicMax(&th[lane], hm);
+      } else if (warp == 4) {
+#pragma unroll
+        for (int jj = 0; jj < 8; jj++) c[jj] = (jj < nb) ? Sf[j0 + jj] : 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          const double lk = c[k] * rinv[k];
+#pragma unroll
+          for (int jj = k + 1; jj < 8; jj++) c[jj] -= lk * Wm[jj * 8 + k];
+          c[k] = lk;
+        }
+        __syncwarp();
+        if (lane < 8) {
+          double mine = c[0];
+#pragma unroll
+          for (int jj = 1; jj < 8; jj++) mine = (lane == jj) ? c[jj] : mine;
+          if (lane < nb) Sf[j0 + lane] = mine;
+        }
+      }
+      phase_end(W, 10, tq, 32);
+      tq = phase_begin(W);
+      nbar_sync(BAR_EB + par, NT);
+      phase_end(W, 14, tq, 32);
+      tq = phase_begin(W);
+      // ---- step 1b: panel p+1 -= (solved rows) W'^T ----
+      if (has1) {
+        if (isK) {
+          if (r < nrows) {
+            if (full) step1_update<true>(L, m, j1, j1 + 8 + r, half, Wp, c);
+            else step1_update<false>(L, m, j1, j1 + 8 + r, half, Wp, c);
+          }
+        } else if (warp == 4) {
+          if (lane < 8 && j1 + lane < m) {
+            double sacc = 0.0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) sacc += c[k] * Wp[lane * 8 + k];
+            Sf[j1 + lane] -= sacc;
+          }
+        }
+      }
+      nbar_sync(BAR_O1, NOTH);
+      phase_end(W, 15, tq, 32);
+      tq = phase_begin(W);
+      // ---- theta check of panel p (all contributions are in) ----
+      {
+        const int jj = lane & 7;
+        const double tub = __hiloint2double(th[jj] + 1, 0);
+        const bool mine = (jj < nb) && !(tub * tub * inv_beta2 * 1.0000001 <= blk[64 + jj]);
+        bad |= __any_sync(0xffffffffu, mine);
+      }
+      if (j2 < m) {
+        // ---- step 2: table D_k L(j2+jj, k), k < j1 ----
+        const int nb2 = min(NB, m - j2);
+        const int total = j1 * NB;
+        for (int e = tid - 32; e < total; e += NOTH) {
+          const int k = e >> 3, jj = e & 7;
+          PB[k * PBS + jj] = (jj < nb2) ? L[coff(k, m) + j2 + jj] * D[k] : 0.0;
+        }
+      }
+      nbar_sync(BAR_O2, NOTH);
+      phase_end(W, 11, tq, 32);
+      tq = phase_begin(W);
+      if (j2 < m && isK) {
+        // ---- step 3: panel p+2 -= L(:, k<j1) table^T ; unit u = sixteen rows j2+16u.. ----
+        const int nb2 = min(NB, m - j2);
+        const int nu = (m - j2 + 15) >> 4;
+        if (widx < nu) {
+          const int ra = j2 + 16 * widx;
+          double c0, c1, u0, u1;
+          old_update16(L, PB, m, j1, tg, g, ra, c0, c1, u0, u1);
+          const int rowA = ra + 2 * g, rowB = rowA + 1;
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            const int col = 2 * tg + h;
+            if (col < nb2) {
+              double* dst = L + coff(j2 + col, m);
+              if (rowA < m && rowA >= j2 + col) dst[rowA] -= (h ? c1 : c0);
+              if (rowB < m && rowB >= j2 + col) dst[rowB] -= (h ? u1 : u0);
+            }
+          }
+        }
+      } else if (j2 < m && warp == 8) {
+        // rhs row: Sf[j2+jj] -= sum_{k<j1} Sf[k] table[k][jj]; lane = (k slice, jj)
+        const int jj = lane & 7, sl = lane >> 3;
+        double acc = 0.0;
+        for (int k = sl; k < j1; k += 4) acc += Sf[k] * PB[k * PBS + jj];
+        acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+        if (lane < 8 && j2 + lane < m) Sf[j2 + lane] -= acc;
+      }
+      phase_end(W, 13, tq, 32);
+      if (p + 1 < np) nbar_arrive(BAR_E3 + par, NT);
+    }
+  }
+  return __syncthreads_or(bad) != 0;
 }
 
 // S <- L^-T S ; dy += S     (second half of ldl.cl:529-536), blocks of 32 columns:

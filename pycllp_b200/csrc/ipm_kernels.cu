@@ -21,8 +21,8 @@ static __device__ __forceinline__ void carve(const Matrix& A, const Scratch& sc,
   if constexpr (VS) {
     W.P = smem + o; o += align16(psz);
     W.tiles = nullptr;
-    v = smem + o; o += align16((size_t)5 * n + nw + 6 * m);
-    W.dg = v + 5 * (size_t)n;   // = W.w (max(n, ldd) doubles): dead between prepare_rhs and step
+    v = smem + o; o += align16((size_t)4 * n + nw + 6 * m);
+    W.dg = v + 4 * (size_t)n;   // = W.w (max(n, ldd) doubles): dead between prepare_rhs and step
   } else {   // large problems: only the reduction scratch and the SYRK macro tiles stay on-chip
     W.tiles = smem + o; o += 2 * TB * LDT;
     W.P = slot + sc.off_P;
@@ -31,8 +31,8 @@ static __device__ __forceinline__ void carve(const Matrix& A, const Scratch& sc,
   }
   W.g1 = W.P;      // gather buffers of A_times2: the panel/stage area is idle then
   W.g2 = W.P + (A.ldd > 0 ? A.ldd : 1);
-  W.x = v; W.z = v + n; W.c = v + 2 * n; W.t = v + 3 * n; W.d = v + 4 * n; W.w = v + 5 * n;
-  double* u = v + 5 * (size_t)n + nw;
+  W.x = v; W.z = v + n; W.t = v + 2 * n; W.d = v + 3 * n; W.w = v + 4 * n; W.c = nullptr;
+  double* u = v + 4 * (size_t)n + nw;
   W.y = u; W.b = u + m; W.dy = u + 2 * m; W.S = u + 3 * m; W.RHS = u + 4 * m; W.D = u + 5 * m;
   if constexpr (LS) W.L = smem + o;
   else W.L = slot + sc.off_L;
@@ -43,8 +43,8 @@ static __device__ __forceinline__ void carve(const Matrix& A, const Scratch& sc,
 template <bool LS, bool VS>
 static __device__ __forceinline__ void ipm_solve_one(const Matrix& A, const Batch& B, Work& W, const Params& p, int q) {
   const int m = A.m, n = A.n, tid = threadIdx.x;
+  W.c = B.c + (size_t)q * n;
   for (int j = tid; j < n; j += NT) {
-    W.c[j] = B.c[(size_t)q * n + j];
     W.x[j] = B.hook ? B.x0[(size_t)q * n + j] : 1.0;   // initialize_xzyw, primal_normal.cl:14-28
     W.z[j] = B.hook ? B.z0[(size_t)q * n + j] : 1.0;
   }
@@ -128,11 +128,11 @@ ldl_hook_kernel(int N, int m, const double* AA, double* Lout, double* Dout, int 
   extern __shared__ __align__(16) double smem[];
   Work W;
   double* s = scratch + (size_t)blockIdx.x * slot;
-  const size_t lsz = (size_t)m * (m + 1) / 2;
+  const size_t lsz = (size_t)m * (m + 1) / 2;   // (output layout: row-major packed, as the reference)
   W.red = smem;
   W.P = s;
   W.L = s + (size_t)2 * m * NB + 512;
-  W.D = W.L + lsz;
+  W.D = W.L + packed_doubles(m);
   W.prof = nullptr;
   for (int q = blockIdx.x; q < N; q += gridDim.x) {
     W.M = const_cast<double*>(AA) + (size_t)q * m * m;
@@ -167,12 +167,12 @@ size_t smem_doubles(const Matrix& A, int L_in_smem, int vec_in_smem) {
   } else {
     o += 2 * TB * LDT;
   }
-  if (L_in_smem) o += (size_t)A.m * (A.m + 1) / 2;
+  if (L_in_smem) o += packed_doubles(A.m);
   return o;
 }
 
 size_t work_area_doubles(const Matrix& A) { return work_area(A); }
-size_t vec_area_doubles(const Matrix& A) { return (size_t)5 * A.n + w_doubles(A) + 6 * A.m; }
+size_t vec_area_doubles(const Matrix& A) { return (size_t)4 * A.n + w_doubles(A) + 6 * A.m; }
 
 typedef void (*solve_kernel_t)(Matrix, Batch, Scratch, Params);
 static solve_kernel_t pick_kernel(int L_in_smem, int vec_in_smem) {

@@ -178,7 +178,6 @@ static __device__ __forceinline__ void form_M_dense_tma(const Matrix& A, Work& W
     else if (segN[2] == 2) chunk_loop(std::integral_constant<int, 2>{});
     else if (segN[2] == 3) chunk_loop(std::integral_constant<int, 3>{});
     else chunk_loop(std::integral_constant<int, 4>{});
-    phase_end(W, 14, tk);
     tk = phase_begin(W);
     // epilogue: tiles -> packed L storage and full M
 #pragma unroll
@@ -200,7 +199,6 @@ static __device__ __forceinline__ void form_M_dense_tma(const Matrix& A, Work& W
         }
       }
     }
-    phase_end(W, 15, tk);
     tk = phase_begin(W);
   }
   __syncthreads();

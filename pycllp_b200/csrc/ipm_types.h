@@ -75,6 +75,18 @@ __host__ __device__
 #endif
 inline size_t w_doubles(const Matrix& A) { return (size_t)(A.ldd > A.n ? A.ldd : A.n); }
 
+// Packed lower triangle, COLUMN-major with every column starting at an EVEN offset (so that
+// 16-byte shared-memory loads of two consecutive rows are always aligned): L(i, j) lives at
+// packed_off(j, m) + i.  Consecutive columns are m-1-j apart, rounded up to even.
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+inline int packed_off(int j, int m) { return j * (m - 1) - ((j * (j - 1)) >> 1) + ((j + 1 - (m & 1)) >> 1); }
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+inline size_t packed_doubles(int m) { return (size_t)m * (m + 1) / 2 + m / 2 + 16; }   // + slack: 16-row loads may run past the last column
+
 struct Batch {
   int N;
   const double *b, *c;     // (N, m), (N, n)
