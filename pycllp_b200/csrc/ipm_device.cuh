@@ -102,6 +102,7 @@ struct Work {
 // Counters accumulate in shared memory (W.red[224..240)) and are flushed once per kernel,
 // so that reading the clock does not put a global round trip on the critical path.
 constexpr int RED_PROF = 224;
+constexpr int RED_KEEP = 208;   // [4] per-iteration scalars parked across solve_normal (ipm_kernels.cu)
 // (Every thread reads the clock -- a branch on threadIdx.x == 0 here would make the code that
 // follows look divergent to the compiler and to the hardware.)
 __device__ __forceinline__ long long phase_begin(const Work& W) {
@@ -458,7 +459,9 @@ static __device__ __forceinline__ void solve_normal(const Matrix& A, Work& W, co
   const int m = A.m, tid = threadIdx.x;
   long long t0 = phase_begin(W);
   if (A.sparse) form_M_sparse(A, W);
-  else if (VS) form_M_dense_tma(A, W);      // operand staged by TMA, needs the shared work area
+  else if (VS)                              // operand staged by TMA, needs the shared work area
+    form_M_dense_tma_call(A.sy_A, A.sy_seg, A.dcols, A.sing_ptr, A.sing_col, A.sing_w, A.m, A.nd, A.ldd,
+                          A.sy_ldm, A.sy_npass, W.d, W.dg, W.P, W.red, W.L, W.M, W.prof);
   else form_M_dense(A, W);                  // large problems: macro-tile SYRK, 20 KB of staging
   __syncthreads();
   phase_end(W, 1, t0);
@@ -517,10 +520,11 @@ static __device__ __forceinline__ void solve_normal(const Matrix& A, Work& W, co
 // Returns through refs. After this W.t holds t = c - A'y + mu/x (the ONE evaluation).
 static __device__ __forceinline__ void prepare_rhs(const Matrix& A, Work& W, double mu, double& normr, double& norms) {
   const int m = A.m, n = A.n, tid = threadIdx.x;
+  const double c_first = (tid < n) ? W.c[tid] : 0.0;   // c comes straight from the batch (global): fetch early
   At_times(A, W.y, W.w);
   double ss = 0.0;
   for (int j = tid; j < n; j += NT) {
-    double v = W.w[j], xj = W.x[j], zj = W.z[j], cj = W.c[j];   // (c: straight from the batch)
+    double v = W.w[j], xj = W.x[j], zj = W.z[j], cj = (j == tid) ? c_first : W.c[j];
     double sig = cj - v + zj;
     ss += sig * sig;
     double tj = cj - v + mu / xj;

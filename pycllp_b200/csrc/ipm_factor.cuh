@@ -720,87 +720,79 @@ __device__ __forceinline__ void nbar_arrive(int id, int nthreads) {
 // that an early arrival for panel p+1 can never be counted into the phase of panel p
 constexpr int BAR_ED = 1, BAR_EB = 3, BAR_E3 = 5, BAR_O1 = 7, BAR_O2 = 8;
 
-// warp 0: rows j1..j1+7 of panel j0 against the eliminated block (Wm, rinv); outputs the
-// scaled rows to L storage and Lb[8][8], the unscaled ones (D_k l_k) to Wp[8][8]; then the
-// diagonal tile of panel j1 -= Lb Wp^T (two DMMAs).
+constexpr int PBS = 12;     // row stride of the multiplier tables: the four k-rows of a DMMA B fragment
+                            // (8 doubles each) then fall into disjoint shared-memory banks
+
+// warp 0: the eight rows j1..j1+7 of panel j0 against the eliminated block (Wm, rinv), two
+// entries per lane (row = lane & 7, columns 2cg and 2cg+1 with cg = lane >> 3), the column-k
+// multiplier broadcast by one shuffle per step.  Outputs: the scaled rows to L storage, the
+// unscaled ones (D_k l_k) as the 8-column multiplier table Wp[k][row] (stride PBS); then the
+// diagonal tile of panel j1 -= L(block, panel j0) Wp (two DMMAs).
 static __device__ __forceinline__ void block_row(int m, int j0, int nb, Work& W, const double* Wm,
-                                                 const double* rinv, int* th, double* Wp, double* Lb) {
+                                                 const double* rinv, int* th, double* Wp) {
+  const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
   double* __restrict__ L = W.L;
   const int j1 = j0 + 8;
-  const int row = j1 + lane;
-  const bool valid = lane < 8 && row < m;
+  const int r = lane & 7, cg = lane >> 3;
+  const int row = j1 + r;
+  const bool valid = row < m;
   const int rs = valid ? row : j0;           // (always a valid address)
-  double c[8], un[8];
-  int hm[8];
-#pragma unroll
-  for (int jj = 0; jj < 8; jj++) {
-    const double v = L[coff(min(j0 + jj, m - 1), m) + rs];
-    c[jj] = (valid && jj < nb) ? v : 0.0;
-  }
+  const int ca = coff(min(j0 + 2 * cg, m - 1), m), cb = coff(min(j0 + 2 * cg + 1, m - 1), m);
+  double c0 = (valid && 2 * cg < nb) ? L[ca + rs] : 0.0;
+  double c1 = (valid && 2 * cg + 1 < nb) ? L[cb + rs] : 0.0;
+  int hmine = 0;
 #pragma unroll
   for (int k = 0; k < 8; k++) {
-    hm[k] = dbl_hi(c[k]) & 0x7fffffff;
-    un[k] = c[k];
-    const double lk = c[k] * rinv[k];
-#pragma unroll
-    for (int jj = k + 1; jj < 8; jj++) c[jj] -= lk * Wm[jj * 8 + k];
-    c[k] = lk;
-  }
-  if (lane < 8) {
-#pragma unroll
-    for (int jj = 0; jj < 8; jj++) {
-      Wp[lane * 8 + jj] = un[jj];
-      Lb[lane * 8 + jj] = c[jj];
-      if (valid && jj < nb) L[coff(j0 + jj, m) + row] = c[jj];
+    const double ck = __shfl_sync(FULL, (k & 1) ? c1 : c0, r + 8 * (k >> 1));
+    const int hk = __reduce_max_sync(FULL, dbl_hi(ck) & 0x7fffffff);
+    if (lane == k) hmine = hk;
+    const double lk = ck * rinv[k];
+    if (2 * cg > k) c0 = fma(-lk, Wm[(2 * cg) * 8 + k], c0);
+    if (2 * cg + 1 > k) c1 = fma(-lk, Wm[(2 * cg + 1) * 8 + k], c1);
+    if (cg == (k >> 1)) {
+      Wp[k * PBS + r] = ck;
+      if (k & 1) c1 = lk; else c0 = lk;
     }
   }
-  {
-    int mine = 0;
-#pragma unroll
-    for (int jj = 0; jj < 8; jj++) {
-      const int r = __reduce_max_sync(0xffffffffu, hm[jj]);
-      if (lane == jj) mine = r;
-    }
-    if (lane < 8) th[lane] = max(th[lane], mine);      // only warp 0 touches th before E1
-  }
+  if (valid && 2 * cg < nb) L[ca + row] = c0;
+  if (valid && 2 * cg + 1 < nb) L[cb + row] = c1;
+  if (lane < 8) atomicMax(&th[lane], hmine);          // (the other warps add their rows concurrently)
   __syncwarp();
-  if (j1 < m) {
-    double c0 = 0.0, c1 = 0.0;
-    dmma884(c0, c1, Lb[g * 8 + tg], Wp[g * 8 + tg]);
-    dmma884(c0, c1, Lb[g * 8 + 4 + tg], Wp[g * 8 + 4 + tg]);
+  {
+    const int ra = (j1 + g < m) ? j1 + g : j0;
+    double d0 = 0.0, d1 = 0.0;
+    dmma884(d0, d1, L[coff(j0 + tg, m) + ra], Wp[tg * PBS + g]);
+    dmma884(d0, d1, L[coff(min(j0 + 4 + tg, m - 1), m) + ra], Wp[(4 + tg) * PBS + g]);
     const int r2 = j1 + g;
 #pragma unroll
     for (int h = 0; h < 2; h++) {
       const int col = 2 * tg + h;
-      if (r2 < m && col <= g) L[coff(j1 + col, m) + r2] -= (h ? c1 : c0);
+      if (r2 < m && col <= g) L[coff(j1 + col, m) + r2] -= (h ? d1 : d0);
     }
   }
   __syncwarp();
 }
 
-// Step 3 of factor_ldl_ahead for one warp: a unit of SIXTEEN rows ra..ra+15 against the
-// multiplier table (row stride PBS = 12: the four k-rows of a B fragment fall into disjoint
-// banks).  One 16-byte load per lane brings rows ra+2g and ra+2g+1 of column k -- two
-// interleaved 8-row tiles (even rows / odd rows) -- and every column is a run of sixteen
-// consecutive doubles, i.e. exactly one conflict-free wavefront (the packed layout keeps
-// column starts even).  Two split-K chains per tile; operands of the next step are loaded
-// before the DMMAs of the current one.  K = 8, 16, ...  Rows past the end of a column read
-// whatever follows (finite or not, a DMMA row only feeds the same row of the result, which
-// is then not stored).
-constexpr int PBS = 12;
+// Sixteen rows ra..ra+15 against a multiplier table (row stride PBS), columns k0 .. k0+K-1 of
+// L.  One 16-byte load per lane brings rows ra+2g and ra+2g+1 of a column -- two interleaved
+// 8-row tiles (even rows / odd rows) -- and every column is a run of sixteen consecutive
+// doubles, i.e. exactly one conflict-free wavefront (the packed layout keeps column starts
+// even).  Two split-K chains per tile; operands of the next step are loaded before the DMMAs
+// of the current one.  K = 8, 16, ...  Rows past the end of a column read whatever follows (a
+// DMMA row only feeds the same row of the result, which is then not stored).
 __device__ __forceinline__ void old_update16(const double* __restrict__ L, const double* __restrict__ PB,
-                                             int m, int K, int tg, int g, int ra, double& c0, double& c1,
-                                             double& u0, double& u1) {
+                                             int m, int k0, int K, int tg, int g, int ra, double& c0,
+                                             double& c1, double& u0, double& u1) {
   double e0 = 0.0, e1 = 0.0, v0 = 0.0, v1 = 0.0;
   c0 = c1 = u0 = u1 = 0.0;
-  const double* pa = L + coff(tg, m) + ra + 2 * g;
-  int d = 4 * m - 8 - 4 * tg;                   // coff(k + 4) - coff(k); decreases by 16 per step
+  const double* pa = L + coff(k0 + tg, m) + ra + 2 * g;
+  int d = 4 * m - 8 - 4 * (k0 + tg);            // coff(k + 4) - coff(k); decreases by 16 per step
   const double* pb = PB + tg * PBS + g;
   double2 a1 = *reinterpret_cast<const double2*>(pa); pa += d; d -= 16;
   double2 a2 = *reinterpret_cast<const double2*>(pa); pa += d; d -= 16;
   double b1 = pb[0], b2 = pb[4 * PBS]; pb += 8 * PBS;
-  for (int k0 = 8; k0 < K; k0 += 8) {
+  for (int kk = 8; kk < K; kk += 8) {
     const double2 n1 = *reinterpret_cast<const double2*>(pa); pa += d; d -= 16;
     const double2 n2 = *reinterpret_cast<const double2*>(pa); pa += d; d -= 16;
     const double m1 = pb[0], m2 = pb[4 * PBS]; pb += 8 * PBS;
@@ -816,19 +808,36 @@ __device__ __forceinline__ void old_update16(const double* __restrict__ L, const
   dmma884(v0, v1, a2.y, b2);
   c0 += e0; c1 += e1; u0 += v0; u1 += v1;
 }
+// panel jc (nbc columns), rows ra+2g / ra+2g+1  -=  the accumulators of old_update16
+__device__ __forceinline__ void sub_unit16(double* __restrict__ L, int m, int jc, int nbc, int ra, int g,
+                                           int tg, double c0, double c1, double u0, double u1) {
+  const int rowA = ra + 2 * g, rowB = rowA + 1;
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    const int col = 2 * tg + h;
+    if (col < nbc) {
+      double* dst = L + coff(jc + col, m);
+      if (rowA < m && rowA >= jc + col) dst[rowA] -= (h ? c1 : c0);
+      if (rowB < m && rowB >= jc + col) dst[rowB] -= (h ? u1 : u0);
+    }
+  }
+}
 
-// Step 1 of factor_ldl_ahead for one row, two threads per row.  Part a: solve the row
-// against the eliminated block (both threads, thread `half == 0` stores); part b: subtract
-// the row's product with W' from four of the eight columns of the next panel.
+// Step 1a of factor_ldl_ahead for one row (two threads per row do the same work, thread
+// `half == 0` stores): solve the row against the eliminated block.  tab != nullptr: the row
+// belongs to block p+2, its unscaled entries D_k l_k are the new columns of that block's
+// multiplier table.
 template <bool FULL>
 __device__ __forceinline__ void step1_solve(double* __restrict__ L, int m, int j0, int nb, int row, int half,
                                             const double* __restrict__ Wm, const double* __restrict__ rinv,
-                                            double (&c)[8], int (&hmax)[8]) {
+                                            double* __restrict__ tab, int (&hmax)[8]) {
+  double c[8];
 #pragma unroll
   for (int jj = 0; jj < 8; jj++) c[jj] = (FULL || jj < nb) ? L[coff(min(j0 + jj, m - 1), m) + row] : 0.0;
 #pragma unroll
   for (int k = 0; k < 8; k++) {
     hmax[k] = max(hmax[k], dbl_hi(c[k]) & 0x7fffffff);
+    if (tab != nullptr && half == 0) tab[k * PBS] = c[k];
     const double lk = c[k] * rinv[k];
 #pragma unroll
     for (int jj = k + 1; jj < 8; jj++) c[jj] -= lk * Wm[jj * 8 + k];
@@ -840,20 +849,6 @@ __device__ __forceinline__ void step1_solve(double* __restrict__ L, int m, int j
       if (FULL || jj < nb) L[coff(min(j0 + jj, m - 1), m) + row] = c[jj];
   }
 }
-template <bool FULL>
-__device__ __forceinline__ void step1_update(double* __restrict__ L, int m, int j1, int row, int half,
-                                             const double* __restrict__ Wp, const double (&c)[8]) {
-  const int nb1 = min(NB, m - j1);
-#pragma unroll
-  for (int q = 0; q < 4; q++) {
-    const int jj = 4 * half + q;
-    const double2* __restrict__ w2 = reinterpret_cast<const double2*>(Wp + jj * 8);
-    const double2 w01 = w2[0], w23 = w2[1], w45 = w2[2], w67 = w2[3];
-    const double s = ((c[0] * w01.x + c[1] * w01.y) + (c[2] * w23.x + c[3] * w23.y)) +
-                     ((c[4] * w45.x + c[5] * w45.y) + (c[6] * w67.x + c[7] * w67.y));
-    if (FULL || jj < nb1) L[coff(min(j1 + jj, m - 1), m) + row] -= s;
-  }
-}
 
 static __device__ __forceinline__ bool factor_ldl_ahead(int m, Work& W, double beta, double delta,
                                                         const double* __restrict__ rhs,
@@ -862,11 +857,10 @@ static __device__ __forceinline__ bool factor_ldl_ahead(int m, Work& W, double b
   const int g = lane >> 2, tg = lane & 3;
   double* __restrict__ L = W.L;
   double* __restrict__ D = W.D;
-  double* PB = W.P;                                   // multiplier table [k][8]
-  double* xtra = W.P + (size_t)2 * m * NB;            // 512 spare doubles of the work area
+  const int TBL = PBS * max(8, m - 16);               // one multiplier table [k][PBS]
+  double* xtra = W.P + 2 * TBL;                       // 512 more doubles of the work area
   // per-parity block data at xtra + 80 par: Wm[64], D1[8], rinv[8]
-  double* Wp = xtra + 160;                            // D_k L(block p+1, panel p)   [8][8]
-  double* Lb = xtra + 224;                            // L(block p+1, panel p)       [8][8]
+  double* Wp = xtra + 160;                            // D_k L(block p+1, panel p)   [k][PBS]
   int* thbuf = reinterpret_cast<int*>(W.red + RED_TH);
   const double inv_beta2 = 1.0 / (beta * beta);
   const int np = (m + 7) >> 3;
@@ -896,37 +890,39 @@ static __device__ __forceinline__ bool factor_ldl_ahead(int m, Work& W, double b
       if (p > 0) nbar_sync(BAR_E3 + (par ^ 1), NT);   // others are done with panel p-1
       phase_end(W, 12, tw);
       const long long tr = phase_begin(W);
-      if (j0 + 8 < m) block_row(m, j0, nb, W, blk, blk + 72, th, Wp, Lb);
+      if (j0 + 8 < m) block_row(m, j0, nb, W, blk, blk + 72, th, Wp);
       nbar_arrive(BAR_EB + par, NT);                  // W' of panel p published
       phase_end(W, 8, tr);
     }
   } else {
     // ------------------------------ everything else -------------------------------
-    const int t = widx * 32 + lane;                   // slot of the DMMA warps' threads
-    const int r = t >> 1, half = t & 1;               // step 1: two threads per row
+    // step 1: DMMA warp widx owns the sixteen rows j2 + 16 widx .. +15, two threads per row
+    const int r = widx * 16 + (lane >> 1), half = lane & 1;
     for (int p = 0; p < np; p++) {
-      const int j0 = 8 * p, j1 = j0 + 8, j2 = j0 + 16;
+      const int j0 = 8 * p, j1 = j0 + 8, j2 = j0 + 16, j3 = j0 + 24;
       const int nb = min(NB, m - j0), par = p & 1;
       const double* blk = xtra + 80 * par;
       const double* Wm = blk;
       const double* rinv = blk + 72;
       int* th = thbuf + par * 8;
-      const int nrows = max(0, m - j1 - 8);
-      const bool has1 = j1 < m;
-      const bool full = (nb == NB) && (!has1 || m - j1 >= NB);
+      double* PBcur = W.P + par * TBL;                // table of panel p+2 (used in step 3)
+      double* PBnxt = W.P + (par ^ 1) * TBL;          // table of panel p+3 (old part built here)
+      const int nrows = max(0, m - j2);
+      const bool full = (nb == NB) && (m - j1 >= NB || j1 >= m);
       long long tq = phase_begin(W);
       nbar_sync(BAR_ED + par, NT);
       phase_end(W, 7, tq, 32);
       tq = phase_begin(W);
       // ---- step 1a: solve the rows below block p+1 against block p; rhs row on warp 4 ----
-      double c[8];
+      double crhs[8];
       if (isK) {
         int hmax[8];
 #pragma unroll
         for (int jj = 0; jj < 8; jj++) hmax[jj] = 0;
         if (r < nrows) {
-          if (full) step1_solve<true>(L, m, j0, nb, j1 + 8 + r, half, Wm, rinv, c, hmax);
-          else step1_solve<false>(L, m, j0, nb, j1 + 8 + r, half, Wm, rinv, c, hmax);
+          double* tab = (r < 8) ? PBcur + j0 * PBS + r : nullptr;   // rows of block p+2
+          if (full) step1_solve<true>(L, m, j0, nb, j2 + r, half, Wm, rinv, tab, hmax);
+          else step1_solve<false>(L, m, j0, nb, j2 + r, half, Wm, rinv, tab, hmax);
         }
         int hm = 0;
 #pragma unroll
@@ -937,94 +933,85 @@ static __device__ __forceinline__ bool factor_ldl_ahead(int m, Work& W, double b
         if (lane < 8 && hm > 0) atomicMax(&th[lane], hm);
       } else if (warp == 4) {
 #pragma unroll
-        for (int jj = 0; jj < 8; jj++) c[jj] = (jj < nb) ? Sf[j0 + jj] : 0.0;
+        for (int jj = 0; jj < 8; jj++) crhs[jj] = (jj < nb) ? Sf[j0 + jj] : 0.0;
 #pragma unroll
         for (int k = 0; k < 8; k++) {
-          const double lk = c[k] * rinv[k];
+          const double lk = crhs[k] * rinv[k];
 #pragma unroll
-          for (int jj = k + 1; jj < 8; jj++) c[jj] -= lk * Wm[jj * 8 + k];
-          c[k] = lk;
+          for (int jj = k + 1; jj < 8; jj++) crhs[jj] -= lk * Wm[jj * 8 + k];
+          crhs[k] = lk;
         }
         __syncwarp();
         if (lane < 8) {
-          double mine = c[0];
+          double mine = crhs[0];
 #pragma unroll
-          for (int jj = 1; jj < 8; jj++) mine = (lane == jj) ? c[jj] : mine;
+          for (int jj = 1; jj < 8; jj++) mine = (lane == jj) ? crhs[jj] : mine;
           if (lane < nb) Sf[j0 + lane] = mine;
         }
       }
+      nbar_sync(BAR_O1, NOTH);                        // all rows solved, table of panel p+2 complete
       phase_end(W, 10, tq, 32);
       tq = phase_begin(W);
-      nbar_sync(BAR_EB + par, NT);
-      phase_end(W, 14, tq, 32);
-      tq = phase_begin(W);
-      // ---- step 1b: panel p+1 -= (solved rows) W'^T ----
-      if (has1) {
+      // ---- theta check of panel p (all contributions are in: warp 0's came before BAR_ED..EB
+      // of this panel at the latest -- checked again after BAR_EB below) ----
+      if (j2 < m) {
         if (isK) {
-          if (r < nrows) {
-            if (full) step1_update<true>(L, m, j1, j1 + 8 + r, half, Wp, c);
-            else step1_update<false>(L, m, j1, j1 + 8 + r, half, Wp, c);
+          // ---- step 2: panel p+2 -= L(:, k<j1) table^T ; unit u = sixteen rows j2+16u.. ----
+          if (16 * widx < nrows) {
+            const int ra = j2 + 16 * widx;
+            double c0, c1, u0, u1;
+            old_update16(L, PBcur, m, 0, j1, tg, g, ra, c0, c1, u0, u1);
+            sub_unit16(L, m, j2, min(NB, m - j2), ra, g, tg, c0, c1, u0, u1);
           }
-        } else if (warp == 4) {
-          if (lane < 8 && j1 + lane < m) {
-            double sacc = 0.0;
-#pragma unroll
-            for (int k = 0; k < 8; k++) sacc += c[k] * Wp[lane * 8 + k];
-            Sf[j1 + lane] -= sacc;
+        } else {
+          if (warp == 8) {
+            // rhs row: Sf[j2+jj] -= sum_{k<j1} Sf[k] table[k][jj]; lane = (k slice, jj)
+            const int jj = lane & 7, sl = lane >> 3;
+            double acc = 0.0;
+            for (int k = sl; k < j1; k += 4) acc += Sf[k] * PBcur[k * PBS + jj];
+            acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+            if (lane < 8 && j2 + lane < m) Sf[j2 + lane] -= acc;
+          }
+          // ---- the old part of the NEXT table (panel p+3): D_k L(j3+jj, k), k < j1 ----
+          if (j3 < m) {
+            const int total = j1 * NB;
+            for (int e = (warp >> 2) * 32 + lane - 32; e < total; e += 96) {
+              const int k = e >> 3, jj = e & 7;
+              PBnxt[k * PBS + jj] = (j3 + jj < m) ? L[coff(k, m) + j3 + jj] * D[k] : 0.0;
+            }
           }
         }
       }
-      nbar_sync(BAR_O1, NOTH);
-      phase_end(W, 15, tq, 32);
+      phase_end(W, 13, tq, 32);
       tq = phase_begin(W);
-      // ---- theta check of panel p (all contributions are in) ----
+      nbar_sync(BAR_EB + par, NT);                    // W' of panel p (warp 0 published it long ago)
+      phase_end(W, 14, tq, 32);
+      tq = phase_begin(W);
       {
         const int jj = lane & 7;
         const double tub = __hiloint2double(th[jj] + 1, 0);
         const bool mine = (jj < nb) && !(tub * tub * inv_beta2 * 1.0000001 <= blk[64 + jj]);
         bad |= __any_sync(0xffffffffu, mine);
       }
-      if (j2 < m) {
-        // ---- step 2: table D_k L(j2+jj, k), k < j1 ----
-        const int nb2 = min(NB, m - j2);
-        const int total = j1 * NB;
-        for (int e = tid - 32; e < total; e += NOTH) {
-          const int k = e >> 3, jj = e & 7;
-          PB[k * PBS + jj] = (jj < nb2) ? L[coff(k, m) + j2 + jj] * D[k] : 0.0;
-        }
-      }
-      nbar_sync(BAR_O2, NOTH);
-      phase_end(W, 11, tq, 32);
-      tq = phase_begin(W);
-      if (j2 < m && isK) {
-        // ---- step 3: panel p+2 -= L(:, k<j1) table^T ; unit u = sixteen rows j2+16u.. ----
-        const int nb2 = min(NB, m - j2);
-        const int nu = (m - j2 + 15) >> 4;
-        if (widx < nu) {
-          const int ra = j2 + 16 * widx;
-          double c0, c1, u0, u1;
-          old_update16(L, PB, m, j1, tg, g, ra, c0, c1, u0, u1);
-          const int rowA = ra + 2 * g, rowB = rowA + 1;
+      // ---- step 3: panel p+1 -= (solved rows) W' : each DMMA warp for its own sixteen rows ----
+      if (j1 < m) {
+        if (isK) {
+          if (16 * widx < nrows) {
+            double c0, c1, u0, u1;
+            old_update16(L, Wp, m, j0, 8, tg, g, j2 + 16 * widx, c0, c1, u0, u1);
+            sub_unit16(L, m, j1, min(NB, m - j1), j2 + 16 * widx, g, tg, c0, c1, u0, u1);
+          }
+        } else if (warp == 4) {
+          if (lane < 8 && j1 + lane < m) {
+            double sacc = 0.0;
 #pragma unroll
-          for (int h = 0; h < 2; h++) {
-            const int col = 2 * tg + h;
-            if (col < nb2) {
-              double* dst = L + coff(j2 + col, m);
-              if (rowA < m && rowA >= j2 + col) dst[rowA] -= (h ? c1 : c0);
-              if (rowB < m && rowB >= j2 + col) dst[rowB] -= (h ? u1 : u0);
-            }
+            for (int k = 0; k < 8; k++) sacc += crhs[k] * Wp[k * PBS + lane];
+            Sf[j1 + lane] -= sacc;
           }
         }
-      } else if (j2 < m && warp == 8) {
-        // rhs row: Sf[j2+jj] -= sum_{k<j1} Sf[k] table[k][jj]; lane = (k slice, jj)
-        const int jj = lane & 7, sl = lane >> 3;
-        double acc = 0.0;
-        for (int k = sl; k < j1; k += 4) acc += Sf[k] * PB[k * PBS + jj];
-        acc += __shfl_xor_sync(0xffffffffu, acc, 8);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 16);
-        if (lane < 8 && j2 + lane < m) Sf[j2 + lane] -= acc;
       }
-      phase_end(W, 13, tq, 32);
+      phase_end(W, 15, tq, 32);
       if (p + 1 < np) nbar_arrive(BAR_E3 + par, NT);
     }
   }

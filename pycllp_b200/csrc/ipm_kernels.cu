@@ -78,12 +78,15 @@ static __device__ __forceinline__ void ipm_solve_one(const Matrix& A, const Batc
     if (normr < p.eps && norms < p.eps && gamma < p.eps) { stat = 0; break; }   // :256-259
     if (normr > 10 * normr0 && normr > p.eps) { stat = 2; break; }              // :261-264
     if (norms > 10 * norms0 && norms > p.eps) { stat = 4; break; }              // :266-269
+    // the iteration's scalars wait in shared memory while the tensor-core phases run: the SYRK
+    // and factor loops need every register they can get (block-uniform values, benign race)
+    W.red[RED_KEEP] = normr; W.red[RED_KEEP + 1] = norms; W.red[RED_KEEP + 2] = mu;
     solve_normal<LS, VS>(A, W, p);
     t0 = phase_begin(W);
-    step(A, W, mu, p.r);
+    step(A, W, W.red[RED_KEEP + 2], p.r);
     phase_end(W, 5, t0);
-    normr0 = normr;
-    norms0 = norms;
+    normr0 = W.red[RED_KEEP];
+    norms0 = W.red[RED_KEEP + 1];
   }
   if (B.x) for (int j = tid; j < n; j += NT) B.x[(size_t)q * n + j] = W.x[j];
   if (B.z) for (int j = tid; j < n; j += NT) B.z[(size_t)q * n + j] = W.z[j];

@@ -47,6 +47,12 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
       : "memory");
 }
 
+// 8-byte shared-memory load that keeps its place in the instruction stream
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
 // shared-memory counter: release this thread's (warp's, after __syncwarp) earlier accesses,
 // acquire those of the threads that incremented before
 __device__ __forceinline__ int atom_add_acq_rel(int* p, int v) {
@@ -71,19 +77,30 @@ __device__ __forceinline__ void syrk_chunk(double (&acc)[SY_SEG][SY_CW][2], cons
     const double dk = dgc[ks * 4 + tg];
     const double* __restrict__ col = S + (ks * 4 + tg) * ldm + g;
     if constexpr (N2 >= 0) {
-      double as[SY_SEG];
+      // explicit software pipeline (volatile loads keep their program order): ptxas otherwise
+      // tends to funnel all B fragments through ONE register pair, load -> DMMA -> load ..., which
+      // exposes the shared-memory latency on every DMMA
+      const uint32_t cb = smem_u32(col);
+      double as[SY_SEG], b0[SY_CW], b1[SY_CW], b2[SY_CW];
 #pragma unroll
-      for (int s = 0; s < SY_SEG; s++) as[s] = col[8 * segI[s]] * dk;   // (empty segment: tile 0)
+      for (int s = 0; s < SY_SEG; s++) as[s] = lds_f64(cb + 64 * segI[s]);   // (empty segment: tile 0)
 #pragma unroll
-      for (int s = 0; s < SY_SEG; s++) {
+      for (int t = 0; t < SY_CW; t++) b0[t] = lds_f64(cb + 64 * (segJ[0] + t));
 #pragma unroll
-        for (int t = 0; t < SY_CW; t++) {
-          if (s < SY_SEG - 1 || t < N2) {
-            const double b = col[8 * (segJ[s] + t)];
-            dmma884(acc[s][t][0], acc[s][t][1], as[s], b);
-          }
-        }
-      }
+      for (int t = 0; t < SY_CW; t++) b1[t] = lds_f64(cb + 64 * (segJ[1] + t));
+      as[0] *= dk;
+#pragma unroll
+      for (int t = 0; t < SY_CW; t++) dmma884(acc[0][t][0], acc[0][t][1], as[0], b0[t]);
+#pragma unroll
+      for (int t = 0; t < SY_CW; t++)
+        if (t < N2) b2[t] = lds_f64(cb + 64 * (segJ[2] + t));
+      as[1] *= dk;
+#pragma unroll
+      for (int t = 0; t < SY_CW; t++) dmma884(acc[1][t][0], acc[1][t][1], as[1], b1[t]);
+      if (N2 > 0) as[2] *= dk;
+#pragma unroll
+      for (int t = 0; t < SY_CW; t++)
+        if (t < N2) dmma884(acc[2][t][0], acc[2][t][1], as[2], b2[t]);
     } else {
 #pragma unroll
       for (int s = 0; s < SY_SEG; s++) {
@@ -212,6 +229,25 @@ static __device__ __forceinline__ void form_M_dense_tma(const Matrix& A, Work& W
       W.L[coff(i, m) + i] = v;
     }
   }
+}
+
+
+// Out-of-line entry: the SYRK loop needs ~100 registers of its own (12 accumulator tiles,
+// prefetched fragments).  Inlined into the persistent kernel its register allocation is at the
+// mercy of everything that is live around it (seen: the fragment loads collapse onto one
+// register and serialise, +16 % time); as a real function it gets its own allocation and the
+// caller parks its live values around the single call per Newton step.
+static __device__ __noinline__ void form_M_dense_tma_call(
+    const double* sy_A, const int4* sy_seg, const int* dcols, const int* sing_ptr, const int* sing_col,
+    const double* sing_w, int m, int nd, int ldd, int ldm, int npass, double* d, double* dg, double* P,
+    double* red, double* L, double* M, unsigned long long* prof) {
+  Matrix A;
+  A.m = m; A.nd = nd; A.ldd = ldd; A.sy_ldm = ldm; A.sy_npass = npass;
+  A.sy_A = sy_A; A.sy_seg = sy_seg; A.dcols = dcols;
+  A.sing_ptr = sing_ptr; A.sing_col = sing_col; A.sing_w = sing_w;
+  Work W;
+  W.d = d; W.dg = dg; W.P = P; W.red = red; W.L = L; W.M = M; W.prof = prof;
+  form_M_dense_tma(A, W);
 }
 
 }  // namespace pb200
