@@ -831,9 +831,20 @@ template <bool FULL>
 __device__ __forceinline__ void step1_solve(double* __restrict__ L, int m, int j0, int nb, int row, int half,
                                             const double* __restrict__ Wm, const double* __restrict__ rinv,
                                             double* __restrict__ tab, int (&hmax)[8]) {
+  // offsets of the panel's columns (block-uniform, incremental: coff(j+1) - coff(j) = m-1-j
+  // rounded up to even; j0 is a multiple of 8)
+  int cb[8];
+  cb[0] = coff(j0, m);
+  const int e = 1 - (m & 1);
+#pragma unroll
+  for (int jj = 1; jj < 8; jj++) cb[jj] = cb[jj - 1] + (m - j0 - jj) + ((jj - 1 + e) & 1);
+  double* __restrict__ Lr = L + row;
   double c[8];
 #pragma unroll
-  for (int jj = 0; jj < 8; jj++) c[jj] = (FULL || jj < nb) ? L[coff(min(j0 + jj, m - 1), m) + row] : 0.0;
+  for (int jj = 0; jj < 8; jj++) {
+    if (!FULL) cb[jj] = coff(min(j0 + jj, m - 1), m);
+    c[jj] = (FULL || jj < nb) ? Lr[cb[jj]] : 0.0;
+  }
 #pragma unroll
   for (int k = 0; k < 8; k++) {
     hmax[k] = max(hmax[k], dbl_hi(c[k]) & 0x7fffffff);
@@ -846,7 +857,7 @@ __device__ __forceinline__ void step1_solve(double* __restrict__ L, int m, int j
   if (half == 0) {
 #pragma unroll
     for (int jj = 0; jj < 8; jj++)
-      if (FULL || jj < nb) L[coff(min(j0 + jj, m - 1), m) + row] = c[jj];
+      if (FULL || jj < nb) Lr[cb[jj]] = c[jj];
   }
 }
 
@@ -857,7 +868,7 @@ static __device__ __forceinline__ bool factor_ldl_ahead(int m, Work& W, double b
   const int g = lane >> 2, tg = lane & 3;
   double* __restrict__ L = W.L;
   double* __restrict__ D = W.D;
-  const int TBL = PBS * max(8, m - 16);               // one multiplier table [k][PBS]
+  const int TBL = PBS * max(8, m - 8);                // one multiplier table [k][PBS], k < j1 <= m-9
   double* xtra = W.P + 2 * TBL;                       // 512 more doubles of the work area
   // per-parity block data at xtra + 80 par: Wm[64], D1[8], rinv[8]
   double* Wp = xtra + 160;                            // D_k L(block p+1, panel p)   [k][PBS]

@@ -65,7 +65,7 @@ inline size_t work_area(const Matrix& A) {
   size_t psz = (size_t)2 * A.m * NB + 512;
   const size_t st = (size_t)SY_STAGES * SY_KC * A.sy_ldm;
   const size_t g = (size_t)2 * (A.ldd > 0 ? A.ldd : 1);
-  const size_t tb = (size_t)2 * 12 * (A.m > 24 ? A.m - 16 : 8) + 512;   // two tables of factor_ldl_ahead
+  const size_t tb = (size_t)2 * 12 * (A.m > 16 ? A.m - 8 : 8) + 512;   // two tables of factor_ldl_ahead
   if (psz < st) psz = st;
   if (psz < g) psz = g;
   if (psz < tb) psz = tb;

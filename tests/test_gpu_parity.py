@@ -47,8 +47,11 @@ def test_sparse_vs_reference_golden(engine, name):
 def test_dense_vs_oracle_random_shapes(engine, oracle):
     """Ragged shapes: m, n not multiples of the 8-wide tensor-core tiles / 64-wide macro tiles."""
     rng = np.random.RandomState(5)
+    # (the low-rank shapes -- one or two dense columns next to the slacks -- sit on the boundary
+    # of the theta-clamp test of the speculative factorisation and exercise its exact redo;
+    # m = 203 runs the look-ahead factor with a ragged last panel and odd column count)
     for m, n0, dens, N in [(1, 3, 1.0, 4), (7, 5, 1.0, 9), (13, 29, 0.5, 17), (65, 70, 0.3, 12),
-                           (130, 97, 1.0, 6)]:
+                           (130, 97, 1.0, 6), (24, 1, 1.0, 6), (40, 2, 1.0, 5), (203, 60, 1.0, 3)]:
         A0 = rng.rand(m, n0) * (rng.rand(m, n0) < dens)
         A = np.c_[A0, np.eye(m)]
         b = 0.5 + rng.rand(N, m)
@@ -57,6 +60,23 @@ def test_dense_vs_oracle_random_shapes(engine, oracle):
         assert_parity(_dense(engine, A, b, c), ref, c, "dense %dx%d" % (m, n0 + m))
         refs = oracle.solve_sparse(A, b, c)
         assert_parity(_sparse(engine, A, b, c), refs, c, "sparse %dx%d" % (m, n0 + m))
+
+
+def test_factor_without_refinement_sweep(engine, oracle):
+    """The sparse solver has no iterative refinement (ldl.cl:698-711), so any error of the
+    factorisation shows up as extra Newton steps or a different status.  Sweep m over the
+    panel/unit boundaries of the look-ahead factor (8-column panels, 16-row units, odd m,
+    the largest m that keeps L in shared memory) and demand identical step counts."""
+    rng = np.random.RandomState(11)
+    for m in (9, 16, 17, 31, 40, 72, 97, 129, 177, 201, 206):
+        n0, N = m // 3 + 1, 2
+        A = np.c_[rng.rand(m, n0), np.eye(m)]
+        b = 0.5 + rng.rand(N, m)
+        c = np.c_[0.5 + rng.rand(N, n0), np.zeros((N, m))]
+        ref = oracle.solve_sparse(A, b, c)
+        res = _sparse(engine, A, b, c)
+        assert_parity(res, ref, c, "sparse, dense A, m=%d" % m)
+        np.testing.assert_array_equal(res["iters"], ref.iters, err_msg="m=%d" % m)
 
 
 def test_known_answers_through_the_plugin_api(engine):
