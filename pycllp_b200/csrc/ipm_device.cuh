@@ -96,6 +96,7 @@ struct Work {
   double* M;                            // m*m full symmetric (global scratch)
   double* red;                          // 256: reductions [0,32) + panel scratch (ipm_factor.cuh)
   unsigned long long* prof;             // per-phase cycle counters of this block (or null)
+  int ring_g;                           // chunks that have gone through the TMA ring so far (ipm_syrk.cuh)
 };
 
 // phase ids: 0 rhs/norms, 1 form M, 2 factor, 3 triangular solves, 4 residual, 5 step
@@ -180,7 +181,7 @@ __device__ __forceinline__ void At_times(const Matrix& A, const double* __restri
       for (int i = lane; i < m; i += 32) {
         const double ui = u[i];
 #pragma unroll
-        for (int c = 0; c < 8; c++) a[c] += p[c * ldm + i] * ui;
+        for (int c = 0; c < 8; c++) a[c] += __ldcg(p + c * ldm + i) * ui;
       }
       const double t = warp_sum8(a, lane);
       if ((lane & 3) == 0 && k0 + q < A.nd) out[A.dcols[k0 + q]] = t;
@@ -242,7 +243,7 @@ __device__ __forceinline__ void A_times2(const Matrix& A, const double* __restri
 #pragma unroll 2
       for (int k = lane; k < ldd; k += 32) {
         const double x = g1[k], w = g2[k];
-        const double v0 = r0[k], v1 = r1[k], v2 = r2[k], v3 = r3[k];
+        const double v0 = __ldcg(r0 + k), v1 = __ldcg(r1 + k), v2 = __ldcg(r2 + k), v3 = __ldcg(r3 + k);
         a[0] += v0 * x; a[1] += v0 * w;
         a[2] += v1 * x; a[3] += v1 * w;
         a[4] += v2 * x; a[5] += v2 * w;
@@ -441,7 +442,7 @@ static __device__ __forceinline__ double residual_M(int m, Work& W) {
     for (int j = lane; j < m; j += 32) {
       const double v = W.dy[j];
 #pragma unroll
-      for (int c = 0; c < 8; c++) a[c] += r[c][j] * v;
+      for (int c = 0; c < 8; c++) a[c] += __ldcg(r[c] + j) * v;
     }
     const double t = warp_sum8(a, lane);
     if ((lane & 3) == 0 && i0 + q < m) {
@@ -460,8 +461,9 @@ static __device__ __forceinline__ void solve_normal(const Matrix& A, Work& W, co
   long long t0 = phase_begin(W);
   if (A.sparse) form_M_sparse(A, W);
   else if (VS)                              // operand staged by TMA, needs the shared work area
-    form_M_dense_tma_call(A.sy_A, A.sy_seg, A.dcols, A.sing_ptr, A.sing_col, A.sing_w, A.m, A.nd, A.ldd,
-                          A.sy_ldm, A.sy_npass, W.d, W.dg, W.P, W.red, W.L, W.M, W.prof);
+    W.ring_g = form_M_dense_tma_call(A.sy_A, A.sy_seg, A.dcols, A.sing_ptr, A.sing_col, A.sing_w, A.m, A.nd,
+                                     A.ldd, A.sy_ldm, A.sy_npass, W.d, W.dg, W.P, W.red, W.L, W.M, W.prof,
+                                     W.ring_g);
   else form_M_dense(A, W);                  // large problems: macro-tile SYRK, 20 KB of staging
   __syncthreads();
   phase_end(W, 1, t0);
@@ -501,7 +503,12 @@ static __device__ __forceinline__ void solve_normal(const Matrix& A, Work& W, co
   back_solve_fast(m, W);
   phase_end(W, 3, t0);
   t0 = phase_begin(W);
-  double maxr = residual_M(m, W);
+#ifdef PB200_STREAM_MATVEC
+  const bool rstream = VS && !A.sparse;
+#else
+  const bool rstream = false;
+#endif
+  double maxr = rstream ? residual_stream(m, W) : residual_M(m, W);
   phase_end(W, 4, t0);
   int nref = 0;
   while (maxr > p.refine_tol && nref < p.max_refine) {
@@ -510,7 +517,7 @@ static __device__ __forceinline__ void solve_normal(const Matrix& A, Work& W, co
     back_solve_fast(m, W);
     phase_end(W, 3, t0);
     t0 = phase_begin(W);
-    maxr = residual_M(m, W);
+    maxr = rstream ? residual_stream(m, W) : residual_M(m, W);
     phase_end(W, 4, t0);
     nref++;
   }
@@ -518,10 +525,17 @@ static __device__ __forceinline__ void solve_normal(const Matrix& A, Work& W, co
 
 // Given x, z, y (and mu): v = A'y -> W.w ; t, d ; q -> W.w ; RHS ; also rho/sigma norms.
 // Returns through refs. After this W.t holds t = c - A'y + mu/x (the ONE evaluation).
+template <bool VS>
 static __device__ __forceinline__ void prepare_rhs(const Matrix& A, Work& W, double mu, double& normr, double& norms) {
   const int m = A.m, n = A.n, tid = threadIdx.x;
   const double c_first = (tid < n) ? W.c[tid] : 0.0;   // c comes straight from the batch (global): fetch early
-  At_times(A, W.y, W.w);
+  const bool streamed = VS && !A.sparse && 2 * m <= NT;
+  (void)streamed;
+#ifdef PB200_STREAM_MATVEC
+  if (streamed) At_times_stream(A, W, W.y, W.w);
+  else
+#endif
+    At_times(A, W.y, W.w);
   double ss = 0.0;
   for (int j = tid; j < n; j += NT) {
     double v = W.w[j], xj = W.x[j], zj = W.z[j], cj = (j == tid) ? c_first : W.c[j];
@@ -534,7 +548,11 @@ static __device__ __forceinline__ void prepare_rhs(const Matrix& A, Work& W, dou
   }
   norms = sqrt(block_sum(ss, W.red));          // (syncs: t, d, q visible)
   // S <- A x ; RHS <- A q
-  A_times2(A, W.x, W.w, W.S, W.RHS, W.g1, W.g2);
+#ifdef PB200_STREAM_MATVEC
+  if (streamed) A_times2_stream(A, W, W.x, W.w, W.S, W.RHS, W.g1, W.g2);
+  else
+#endif
+    A_times2(A, W.x, W.w, W.S, W.RHS, W.g1, W.g2);
   double rr = 0.0;
   for (int i = tid; i < m; i += NT) {
     double rho = W.b[i] - W.S[i];
@@ -545,9 +563,14 @@ static __device__ __forceinline__ void prepare_rhs(const Matrix& A, Work& W, dou
 }
 
 // dx, dz, ratio test, update (primal_normal.cl:122-156) using the stored t.
+template <bool VS>
 static __device__ __forceinline__ void step(const Matrix& A, Work& W, double mu, double r) {
   const int m = A.m, n = A.n, tid = threadIdx.x;
-  At_times(A, W.dy, W.w);
+#ifdef PB200_STREAM_MATVEC
+  if (VS && !A.sparse) At_times_stream(A, W, W.dy, W.w);
+  else
+#endif
+    At_times(A, W.dy, W.w);
   double th = 0.0;
   for (int j = tid; j < n; j += NT) {
     double xj = W.x[j], zj = W.z[j];

@@ -29,13 +29,20 @@ static __device__ __forceinline__ void carve(const Matrix& A, const Scratch& sc,
     W.dg = slot + sc.off_dg;
     v = slot + sc.off_vec;
   }
-  W.g1 = W.P;      // gather buffers of A_times2: the panel/stage area is idle then
-  W.g2 = W.P + (A.ldd > 0 ? A.ldd : 1);
+  const size_t ldd1 = (size_t)(A.ldd > 0 ? A.ldd : 1);
+  W.g1 = W.P;      // gather buffers of A_times2 (!VS): the panel/stage area is idle then
+  W.g2 = W.P + ldd1;
   W.x = v; W.z = v + n; W.t = v + 2 * n; W.d = v + 3 * n; W.w = v + 4 * n; W.c = nullptr;
   double* u = v + 4 * (size_t)n + nw;
   W.y = u; W.b = u + m; W.dy = u + 2 * m; W.S = u + 3 * m; W.RHS = u + 4 * m; W.D = u + 5 * m;
   if constexpr (LS) W.L = smem + o;
   else W.L = slot + sc.off_L;
+  if constexpr (VS) {
+    // the streamed A_times2 needs its gather buffers outside the stage ring: the factor's
+    // storage is dead while the right-hand side is prepared; without it, 2 ldd more doubles
+    W.g1 = smem + o;
+    W.g2 = W.g1 + ldd1;
+  }
   W.M = slot;
   W.prof = sc.prof ? sc.prof + (size_t)blockIdx.x * 16 : nullptr;
 }
@@ -56,7 +63,7 @@ static __device__ __forceinline__ void ipm_solve_one(const Matrix& A, const Batc
 
   if (B.hook) {   // one solve_primal_normal (ldl.cl:602-653) on the given state
     double nr, ns;
-    prepare_rhs(A, W, B.mu, nr, ns);
+    prepare_rhs<VS>(A, W, B.mu, nr, ns);
     solve_normal<LS, VS>(A, W, p);
     for (int i = tid; i < m; i += NT) B.dy_out[(size_t)q * m + i] = W.dy[i];
     __syncthreads();
@@ -73,7 +80,7 @@ static __device__ __forceinline__ void ipm_solve_one(const Matrix& A, const Batc
     const double mu = p.delta * gamma / (double)(n + m);          // :272
     double normr, norms;
     long long t0 = phase_begin(W);
-    prepare_rhs(A, W, mu, normr, norms);
+    prepare_rhs<VS>(A, W, mu, normr, norms);
     phase_end(W, 0, t0);
     if (normr < p.eps && norms < p.eps && gamma < p.eps) { stat = 0; break; }   // :256-259
     if (normr > 10 * normr0 && normr > p.eps) { stat = 2; break; }              // :261-264
@@ -83,7 +90,7 @@ static __device__ __forceinline__ void ipm_solve_one(const Matrix& A, const Batc
     W.red[RED_KEEP] = normr; W.red[RED_KEEP + 1] = norms; W.red[RED_KEEP + 2] = mu;
     solve_normal<LS, VS>(A, W, p);
     t0 = phase_begin(W);
-    step(A, W, W.red[RED_KEEP + 2], p.r);
+    step<VS>(A, W, W.red[RED_KEEP + 2], p.r);
     phase_end(W, 5, t0);
     normr0 = W.red[RED_KEEP];
     norms0 = W.red[RED_KEEP + 1];
@@ -106,6 +113,7 @@ ipm_solve_kernel(Matrix A, Batch B, Scratch sc, Params p) {
   Work W;
   carve<LS, VS>(A, sc, smem, W);
   if (W.prof && threadIdx.x < 16) reinterpret_cast<unsigned long long*>(W.red + RED_PROF)[threadIdx.x] = 0;
+  ring_init(W);
   if (A.sparse) {   // entries outside the pattern of A A' are never written again
     const size_t mm = (size_t)A.m * A.m;
     for (size_t e = threadIdx.x; e < mm; e += NT) W.M[e] = 0.0;
@@ -170,7 +178,9 @@ size_t smem_doubles(const Matrix& A, int L_in_smem, int vec_in_smem) {
   } else {
     o += 2 * TB * LDT;
   }
-  if (L_in_smem) o += packed_doubles(A.m);
+  const size_t g = (size_t)2 * (A.ldd > 0 ? A.ldd : 1);
+  if (L_in_smem) o += packed_doubles(A.m) > g ? packed_doubles(A.m) : g;
+  else if (vec_in_smem) o += al(g);
   return o;
 }
 

@@ -13,6 +13,7 @@
 // into W.M for the residual.
 #pragma once
 #include <type_traits>
+#include <cstdio>
 
 namespace pb200 {
 
@@ -28,15 +29,20 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
 }
+// Spin on the barrier's phase.  (C-level loop + __syncwarp so that the lanes are converged
+// again before the warp-collective code that follows.)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
-      : "memory");
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+  __syncwarp();
 }
 // 1-D bulk copy global -> shared, completion counted on an mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -52,6 +58,21 @@ __device__ __forceinline__ double lds_f64(uint32_t addr) {
   double v;
   asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
   return v;
+}
+// The TMA ring (SY_STAGES stages in W.P, one mbarrier + one counter each) is initialised ONCE
+// per kernel: re-initialising a live mbarrier object is undefined behaviour (seen: a hang at
+// one call site).  Every user continues the global chunk count W.ring_g, which fixes stage
+// (g mod SY_STAGES) and phase parity ((g / SY_STAGES) & 1) of every chunk.
+__device__ __forceinline__ void ring_init(Work& W) {
+  uint64_t* full = reinterpret_cast<uint64_t*>(W.red + RED_MBAR);
+  int* done = reinterpret_cast<int*>(full + SY_STAGES);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < SY_STAGES; s++) { mbar_init(&full[s], 1); done[s] = 0; }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  W.ring_g = 0;
+  __syncthreads();
 }
 // shared-memory counter: release this thread's (warp's, after __syncwarp) earlier accesses,
 // acquire those of the threads that incremented before
@@ -134,23 +155,20 @@ static __device__ __forceinline__ void form_M_dense_tma(const Matrix& A, Work& W
   int* done = reinterpret_cast<int*>(full + SY_STAGES);
 
   for (int k = tid; k < A.ldd; k += NT) W.dg[k] = (k < A.nd) ? W.d[A.dcols[k]] : 0.0;
-  if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < SY_STAGES; s++) { mbar_init(&full[s], 1); done[s] = 0; }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
+  const int g0 = W.ring_g;                            // the ring's chunk count so far
   __syncthreads();
   long long tk = phase_begin(W);
   if (tid == 0) {
     // the staging area was last touched through the generic proxy (the factorisation's P)
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     for (int c = 0; c < SY_STAGES && c < total; c++) {
-      mbar_expect_tx(&full[c], chunk_bytes);
-      tma_load_1d(W.P + c * stage_doubles, A.sy_A + (size_t)(c % nch) * stage_doubles, chunk_bytes, &full[c]);
+      const int st = (g0 + c) % SY_STAGES;
+      mbar_expect_tx(&full[st], chunk_bytes);
+      tma_load_1d(W.P + st * stage_doubles, A.sy_A + (size_t)(c % nch) * stage_doubles, chunk_bytes, &full[st]);
     }
   }
 
-  int gch = 0;                                        // global chunk counter over both passes
+  int gch = 0;                                        // chunk counter over both passes
   for (int pass = 0; pass < A.sy_npass; pass++) {
     // this warp's segments: (tile row, first tile col, count)
     int segI[SY_SEG], segJ[SY_SEG], segN[SY_SEG];
@@ -171,8 +189,8 @@ static __device__ __forceinline__ void form_M_dense_tma(const Matrix& A, Work& W
     auto chunk_loop = [&](auto n2c) {
       constexpr int N2 = decltype(n2c)::value;
       for (int ch = 0; ch < nch; ch++, gch++) {
-        const int st = gch % SY_STAGES;
-        mbar_wait(&full[st], (gch / SY_STAGES) & 1);
+        const int st = (g0 + gch) % SY_STAGES;
+        mbar_wait(&full[st], ((g0 + gch) / SY_STAGES) & 1);
         syrk_chunk<N2>(acc, W.P + st * stage_doubles, W.dg + ch * SY_KC, ldm, g, tg, segI, segJ, segN);
         __syncwarp();
         if (lane == 0) {                               // this warp is done with stage st
@@ -218,6 +236,7 @@ static __device__ __forceinline__ void form_M_dense_tma(const Matrix& A, Work& W
     }
     tk = phase_begin(W);
   }
+  W.ring_g = g0 + total;
   __syncthreads();
   // singleton (slack) columns: diagonal only
   for (int i = tid; i < m; i += NT) {
@@ -232,22 +251,187 @@ static __device__ __forceinline__ void form_M_dense_tma(const Matrix& A, Work& W
 }
 
 
+// ---------------------------------------------------------------------------------------
+// Streamed mat-vecs.  Read straight from L2 the three products with A per Newton step and the
+// residual with M were latency-bound (20-35 B/cycle per SM); streamed through the same TMA ring
+// as the SYRK operand the loads are bulk copies with deep memory-level parallelism and the
+// dot products read shared memory.  All 16 warps run the ring protocol for every chunk:
+// wait on the stage's mbarrier, work, count themselves out; the last one refills the stage.
+//   src_of(c) -> global address of chunk c, bytes_of(c) -> its size (multiple of 16), body(S, c).
+// ---------------------------------------------------------------------------------------
+template <class SrcF, class BytesF, class BodyF>
+__device__ __forceinline__ void stream_chunks(Work& W, int total, int stage_doubles, SrcF src_of,
+                                              BytesF bytes_of, BodyF body) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  uint64_t* full = reinterpret_cast<uint64_t*>(W.red + RED_MBAR);
+  int* done = reinterpret_cast<int*>(full + SY_STAGES);
+  const int g0 = W.ring_g;
+  __syncthreads();
+  if (tid == 0) {
+    // the stages were last touched (and the source possibly written) through the generic proxy
+    asm volatile("fence.proxy.async;" ::: "memory");
+    for (int c = 0; c < SY_STAGES && c < total; c++) {
+      const int st = (g0 + c) % SY_STAGES;
+      mbar_expect_tx(&full[st], bytes_of(c));
+      tma_load_1d(W.P + st * stage_doubles, src_of(c), bytes_of(c), &full[st]);
+    }
+  }
+  for (int c = 0; c < total; c++) {
+    const int st = (g0 + c) % SY_STAGES;
+    mbar_wait(&full[st], ((g0 + c) / SY_STAGES) & 1);
+    body(W.P + st * stage_doubles, c);
+    __syncwarp();
+    if (lane == 0) {
+      if (atom_add_acq_rel(&done[st], 1) == NWARP - 1) {
+        done[st] = 0;
+        const int cn = c + SY_STAGES;
+        if (cn < total) {
+          mbar_expect_tx(&full[st], bytes_of(cn));
+          tma_load_1d(W.P + st * stage_doubles, src_of(cn), bytes_of(cn), &full[st]);
+        }
+      }
+    }
+  }
+  W.ring_g = g0 + total;
+  __syncthreads();
+}
+
+// Eight dot products per chunk: chunk c holds vectors 8c..8c+7, `ld` apart, `len` long; warps
+// 0-7 take the even chunks (one vector each), warps 8-15 the odd ones, so two chunks are in
+// work at any time.  emit(index, value) is called by lane 0 of the warp that owns the vector.
+// pre(index) is evaluated before the dot product (e.g. a global table look-up whose latency
+// should not follow the reduction) and handed to emit.
+template <class PreF, class EmitF>
+__device__ __forceinline__ void stream_dots(Work& W, const double* __restrict__ base, int nvec, int ld,
+                                            int len, const double* __restrict__ vec, PreF pre, EmitF emit) {
+  const int lane = threadIdx.x & 31, warp = warp_id();
+  const int total = (nvec + 7) >> 3;
+  const int stage_doubles = SY_KC * ld;
+  auto src_of = [&](int c) { return base + (size_t)c * stage_doubles; };
+  auto bytes_of = [&](int c) {
+    const int nv = min(8, nvec - 8 * c);
+    return (uint32_t)(((size_t)nv * ld * sizeof(double) + 15) & ~(size_t)15);
+  };
+  stream_chunks(W, total, stage_doubles, src_of, bytes_of, [&](const double* __restrict__ S, int c) {
+    if ((c & 1) == (warp >> 3)) {
+      const int k = 8 * c + (warp & 7);
+      if (k < nvec) {
+        const double* __restrict__ col = S + (warp & 7) * ld;
+        const int tok = pre(k);
+        double a0 = 0.0, a1 = 0.0;
+        int i = lane;
+        for (; i + 32 < len; i += 64) {
+          a0 += col[i] * vec[i];
+          a1 += col[i + 32] * vec[i + 32];
+        }
+        if (i < len) a0 += col[i] * vec[i];
+        const double t = warp_sum(a0 + a1);
+        if (lane == 0) emit(k, tok, t);
+      }
+    }
+  });
+}
+
+// out = A' u on the packed operand (columns of A with >= 2 non-zeros), streamed; singleton
+// columns are one multiply.  Ends with __syncthreads().
+__device__ __forceinline__ void At_times_stream(const Matrix& A, Work& W, const double* __restrict__ u,
+                                                double* __restrict__ out) {
+  const int n = A.n, jt = threadIdx.x;
+  int r0 = -2;
+  double cv0 = 0.0;
+  if (jt < n) { r0 = A.colrow[jt]; cv0 = A.colval[jt]; }
+#ifdef PB200_AT_NOPRE
+  stream_dots(W, A.sy_A, A.nd, A.sy_ldm, A.m, u, [](int) { return 0; },
+              [&](int k, int, double t) { out[A.dcols[k]] = t; });
+#else
+  stream_dots(W, A.sy_A, A.nd, A.sy_ldm, A.m, u, [&](int k) { return A.dcols[k]; },
+              [&](int, int j, double t) { out[j] = t; });
+#endif
+  if (jt < n && r0 != -2) out[jt] = (r0 >= 0) ? cv0 * u[r0] : 0.0;
+  for (int j = jt + NT; j < n; j += NT) {
+    const int r = A.colrow[j];
+    if (r != -2) out[j] = (r >= 0) ? A.colval[j] * u[r] : 0.0;
+  }
+  __syncthreads();
+}
+
+// o1 = A u1, o2 = A u2, streamed over the k-major packed operand; two threads per row (each
+// takes four of the eight columns of a chunk).  Requires m <= NT/2.  g1/g2: 2 x ldd doubles
+// outside the stage ring.  Ends with __syncthreads().
+__device__ __forceinline__ void A_times2_stream(const Matrix& A, Work& W, const double* __restrict__ u1,
+                                                const double* __restrict__ u2, double* __restrict__ o1,
+                                                double* __restrict__ o2, double* __restrict__ g1,
+                                                double* __restrict__ g2) {
+  const int m = A.m, ldd = A.ldd, ldm = A.sy_ldm, tid = threadIdx.x;
+  for (int k = tid; k < ldd; k += NT) {
+    const bool ok = k < A.nd;
+    const int j = ok ? A.dcols[k] : 0;
+    g1[k] = ok ? u1[j] : 0.0;
+    g2[k] = ok ? u2[j] : 0.0;
+  }
+  // singleton (slack) columns: one thread per row, added at the end
+  double s1 = 0.0, s2 = 0.0;
+  const int row = tid >> 1, half = tid & 1;
+  if (half == 0 && row < m) {
+    for (int e = A.sing_ptr[row]; e < A.sing_ptr[row + 1]; e++) {
+      const double a = A.sing_a[e];
+      const int j = A.sing_col[e];
+      s1 += a * u1[j];
+      s2 += a * u2[j];
+    }
+  }
+  const int total = ldd / SY_KC;
+  const int stage_doubles = SY_KC * ldm;
+  const uint32_t bytes = (uint32_t)(stage_doubles * sizeof(double));
+  double a1 = 0.0, a2 = 0.0;
+  stream_chunks(W, total, stage_doubles, [&](int c) { return A.sy_A + (size_t)c * stage_doubles; },
+                [&](int) { return bytes; }, [&](const double* __restrict__ S, int c) {
+                  if (row < m) {
+                    const double* __restrict__ p = S + (4 * half) * ldm + row;
+                    const double* __restrict__ x = g1 + c * SY_KC + 4 * half;
+                    const double* __restrict__ q = g2 + c * SY_KC + 4 * half;
+#pragma unroll
+                    for (int kk = 0; kk < 4; kk++) {
+                      const double a = p[kk * ldm];
+                      a1 += a * x[kk];
+                      a2 += a * q[kk];
+                    }
+                  }
+                });
+  a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+  a2 += __shfl_xor_sync(0xffffffffu, a2, 1);
+  if (half == 0 && row < m) { o1[row] = a1 + s1; o2[row] = a2 + s2; }
+  __syncthreads();
+}
+
+// S = RHS - M dy ; returns max |S|, M (row-major, the block's scratch slot) streamed.
+__device__ __forceinline__ double residual_stream(int m, Work& W) {
+  double mx = 0.0;
+  stream_dots(W, W.M, m, m, m, W.dy, [](int) { return 0; }, [&](int i, int, double t) {
+    const double r = W.RHS[i] - t;
+    W.S[i] = r;
+    mx = fmax(mx, fabs(r));
+  });
+  return block_max(mx, W.red);
+}
+
 // Out-of-line entry: the SYRK loop needs ~100 registers of its own (12 accumulator tiles,
 // prefetched fragments).  Inlined into the persistent kernel its register allocation is at the
 // mercy of everything that is live around it (seen: the fragment loads collapse onto one
 // register and serialise, +16 % time); as a real function it gets its own allocation and the
 // caller parks its live values around the single call per Newton step.
-static __device__ __noinline__ void form_M_dense_tma_call(
+static __device__ __noinline__ int form_M_dense_tma_call(
     const double* sy_A, const int4* sy_seg, const int* dcols, const int* sing_ptr, const int* sing_col,
     const double* sing_w, int m, int nd, int ldd, int ldm, int npass, double* d, double* dg, double* P,
-    double* red, double* L, double* M, unsigned long long* prof) {
+    double* red, double* L, double* M, unsigned long long* prof, int ring_g) {
   Matrix A;
   A.m = m; A.nd = nd; A.ldd = ldd; A.sy_ldm = ldm; A.sy_npass = npass;
   A.sy_A = sy_A; A.sy_seg = sy_seg; A.dcols = dcols;
   A.sing_ptr = sing_ptr; A.sing_col = sing_col; A.sing_w = sing_w;
   Work W;
-  W.d = d; W.dg = dg; W.P = P; W.red = red; W.L = L; W.M = M; W.prof = prof;
+  W.d = d; W.dg = dg; W.P = P; W.red = red; W.L = L; W.M = M; W.prof = prof; W.ring_g = ring_g;
   form_M_dense_tma(A, W);
+  return W.ring_g;
 }
 
 }  // namespace pb200
