@@ -525,20 +525,25 @@ static __device__ __forceinline__ void solve_normal(const Matrix& A, Work& W, co
 
 // Given x, z, y (and mu): v = A'y -> W.w ; t, d ; q -> W.w ; RHS ; also rho/sigma norms.
 // Returns through refs. After this W.t holds t = c - A'y + mu/x (the ONE evaluation).
+// have_v: W.t already holds v = A'y, carried over from the previous step as v + theta A'dy
+// (one pass over A less per iteration; an SM only gets 20-35 B/cycle from L2).
 template <bool VS>
-static __device__ __forceinline__ void prepare_rhs(const Matrix& A, Work& W, double mu, double& normr, double& norms) {
+static __device__ __forceinline__ void prepare_rhs(const Matrix& A, Work& W, double mu, double& normr, double& norms,
+                                                   bool have_v = false) {
   const int m = A.m, n = A.n, tid = threadIdx.x;
   const double c_first = (tid < n) ? W.c[tid] : 0.0;   // c comes straight from the batch (global): fetch early
   const bool streamed = VS && !A.sparse && 2 * m <= NT;
   (void)streamed;
+  if (!have_v) {
 #ifdef PB200_STREAM_MATVEC
-  if (streamed) At_times_stream(A, W, W.y, W.w);
-  else
+    if (streamed) At_times_stream(A, W, W.y, W.w);
+    else
 #endif
-    At_times(A, W.y, W.w);
+      At_times(A, W.y, W.w);
+  }
   double ss = 0.0;
   for (int j = tid; j < n; j += NT) {
-    double v = W.w[j], xj = W.x[j], zj = W.z[j], cj = (j == tid) ? c_first : W.c[j];
+    double v = have_v ? W.t[j] : W.w[j], xj = W.x[j], zj = W.z[j], cj = (j == tid) ? c_first : W.c[j];
     double sig = cj - v + zj;
     ss += sig * sig;
     double tj = cj - v + mu / xj;
@@ -562,10 +567,12 @@ static __device__ __forceinline__ void prepare_rhs(const Matrix& A, Work& W, dou
   normr = sqrt(block_sum(rr, W.red));
 }
 
-// dx, dz, ratio test, update (primal_normal.cl:122-156) using the stored t.
+// dx, dz, ratio test, update (primal_normal.cl:122-156) using the stored t.  Leaves
+// v = A'y of the UPDATED y in W.t: v_new = (c - t + mu/x) + theta A'dy.
 template <bool VS>
 static __device__ __forceinline__ void step(const Matrix& A, Work& W, double mu, double r) {
   const int m = A.m, n = A.n, tid = threadIdx.x;
+  const double c_first = (tid < n) ? W.c[tid] : 0.0;
 #ifdef PB200_STREAM_MATVEC
   if (VS && !A.sparse) At_times_stream(A, W, W.dy, W.w);
   else
@@ -577,14 +584,17 @@ static __device__ __forceinline__ void step(const Matrix& A, Work& W, double mu,
     double dx = (W.t[j] - W.w[j]) * xj / zj;
     double dz = (mu - zj * dx) / xj - zj;
     th = fmax(th, fmax(-dz / zj, -dx / xj));
-    W.w[j] = dx;
-    W.t[j] = dz;
+    W.d[j] = dx;                                 // (d = x/z is dead by now; t and w are still needed)
   }
   th = block_max(th, W.red);
   const double theta = fmin(r / th, 1.0);
   for (int j = tid; j < n; j += NT) {
-    W.z[j] += theta * W.t[j];
-    W.x[j] += theta * W.w[j];
+    const double xj = W.x[j], zj = W.z[j], dx = W.d[j];
+    const double dz = (mu - zj * dx) / xj - zj;  // same expression, same operands as above
+    const double cj = (j == tid) ? c_first : W.c[j];
+    W.t[j] = (cj - W.t[j] + mu / xj) + theta * W.w[j];
+    W.z[j] = zj + theta * dz;
+    W.x[j] = xj + theta * dx;
   }
   for (int i = tid; i < m; i += NT) W.y[i] += theta * W.dy[i];
   __syncthreads();

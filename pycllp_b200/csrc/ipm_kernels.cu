@@ -80,7 +80,7 @@ static __device__ __forceinline__ void ipm_solve_one(const Matrix& A, const Batc
     const double mu = p.delta * gamma / (double)(n + m);          // :272
     double normr, norms;
     long long t0 = phase_begin(W);
-    prepare_rhs<VS>(A, W, mu, normr, norms);
+    prepare_rhs<VS>(A, W, mu, normr, norms, iter > 0);
     phase_end(W, 0, t0);
     if (normr < p.eps && norms < p.eps && gamma < p.eps) { stat = 0; break; }   // :256-259
     if (normr > 10 * normr0 && normr > p.eps) { stat = 2; break; }              // :261-264
