@@ -259,6 +259,35 @@ def test_full_size_config3_properties(engine):
     assert 20 <= res["iters"].min() and res["iters"].max() <= 40
 
 
+def _check_optimality(A, b, c, res, what):
+    """Size-independent properties of an optimal primal-dual pair (max c'x, A x = b, x >= 0)."""
+    eps = float(np.float32(1e-7))
+    assert (res["status"] == 0).all(), what
+    x, y, z = res["x"], res["y"], res["z"]
+    At = A.T
+    assert np.linalg.norm(b - (At.T @ x.T).T, axis=1).max() < eps, what
+    assert np.linalg.norm(c - (At @ y.T).T + z, axis=1).max() < eps, what
+    assert np.einsum("ij,ij->i", x, z).max() < eps, what
+    assert x.min() > 0 and z.min() > 0, what
+    np.testing.assert_allclose(objective(x, c), np.einsum("ij,ij->i", y, b), rtol=0, atol=1e-5, err_msg=what)
+
+
+def test_full_size_config5_and_config4_properties(engine):
+    """Configs 5 (dense m=500 n=1000) and 4 (sparse m=2000 n=5000, 1 % + slacks) at their full
+    shapes, one wave of problems each (the batch only repeats the shape): every LP optimal with
+    residuals and gap below the stop tolerance (exact parity at these shapes: the golden cases
+    cfg5_sample and cfg4_small_sparse, test_large_problems_out_of_shared_memory)."""
+    from pycllp_b200.problems import random_equality_arrays, sparse_equality_arrays
+    A, b, c = random_equality_arrays(500, 500, 1.0, 148)
+    res = _dense(engine, A, b, c)
+    _check_optimality(A, b, c, res, "cfg5")
+    assert np.array_equal(A, golden("cfg5_sample")["A"])      # (same A as the exact golden case)
+    As, b, c = sparse_equality_arrays(2000, 3000, 0.01, 16, seed=0)
+    res = _sparse(engine, As, b, c)
+    _check_optimality(As.tocsr(), b, c, res, "cfg4")
+    assert res["iters"].max() <= 80
+
+
 def test_repeat_solves_are_cold_starts_and_deterministic(engine):
     """cl.py:108 re-initialises x = z = y = 1 on every solve; results are reproducible."""
     g = golden("cfg1_dense")
