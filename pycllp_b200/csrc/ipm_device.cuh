@@ -11,7 +11,7 @@
 //   primal_normal.cl:201-284  standard_primal_normal          -> ipm_solve_one
 //   primal_normal.cl:30-120   primal/dual infeasibility       -> stage "residual norms"
 //   ldl.cl:110-138,280-294    A (X/Z) A' entries, beta        -> form_M_dense_tma (ipm_syrk.cuh) / form_M_* (once/iteration)
-//   ldl.cl:314-378            factor_primal_normal            -> factor_ldl_pipe / factor_ldl_fast (ipm_factor.cuh)
+//   ldl.cl:314-378            factor_primal_normal            -> factor_ldl_ahead / factor_ldl_fast (ipm_factor.cuh)
 //   ldl.cl:198-219            primal_normal_rhs_i             -> RHS from the stored t
 //   ldl.cl:505-537            forward_backward_primal_normal  -> forward part inside factor_ldl_*, back_solve_fast
 //   ldl.cl:577-599            residual_primal_normal          -> residual_M
@@ -482,14 +482,10 @@ static __device__ __forceinline__ void solve_normal(const Matrix& A, Work& W, co
   __syncthreads();
   phase_end(W, 6, t0);
   bool redo = true;
-  #ifdef PB200_FACTOR_PIPE
-  if (LS && m <= 8 * 35) redo = factor_ldl_pipe(m, W, beta, p.ldl_delta, W.RHS, W.S);
-#else
-  if (LS && m <= 208) redo = factor_ldl_ahead(m, W, beta, p.ldl_delta, W.RHS, W.S);
-  else if (LS && m <= 8 * 35) redo = factor_ldl_pipe(m, W, beta, p.ldl_delta, W.RHS, W.S);
-#endif
+  const bool ahead = LS && m <= 208;                  // (L in shared memory: m <= ~202 in practice)
+  if (ahead) redo = factor_ldl_ahead(m, W, beta, p.ldl_delta, W.RHS, W.S);
   if (redo) {
-    if (LS && m <= 8 * 35) {     // speculation failed somewhere: restore M and take the exact-capable path
+    if (ahead) {                 // speculation failed somewhere: restore M and take the exact-capable path
       for (int e = tid; e < m * m; e += NT) {
         const int j = e / m, i = e - j * m;
         if (i >= j) W.L[cidx(i, j, m)] = W.M[(size_t)j * m + i];
@@ -503,12 +499,7 @@ static __device__ __forceinline__ void solve_normal(const Matrix& A, Work& W, co
   back_solve_fast(m, W);
   phase_end(W, 3, t0);
   t0 = phase_begin(W);
-#ifdef PB200_STREAM_MATVEC
-  const bool rstream = VS && !A.sparse;
-#else
-  const bool rstream = false;
-#endif
-  double maxr = rstream ? residual_stream(m, W) : residual_M(m, W);
+  double maxr = residual_M(m, W);
   phase_end(W, 4, t0);
   int nref = 0;
   while (maxr > p.refine_tol && nref < p.max_refine) {
@@ -517,7 +508,7 @@ static __device__ __forceinline__ void solve_normal(const Matrix& A, Work& W, co
     back_solve_fast(m, W);
     phase_end(W, 3, t0);
     t0 = phase_begin(W);
-    maxr = rstream ? residual_stream(m, W) : residual_M(m, W);
+    maxr = residual_M(m, W);
     phase_end(W, 4, t0);
     nref++;
   }
@@ -532,15 +523,7 @@ static __device__ __forceinline__ void prepare_rhs(const Matrix& A, Work& W, dou
                                                    bool have_v = false) {
   const int m = A.m, n = A.n, tid = threadIdx.x;
   const double c_first = (tid < n) ? W.c[tid] : 0.0;   // c comes straight from the batch (global): fetch early
-  const bool streamed = VS && !A.sparse && 2 * m <= NT;
-  (void)streamed;
-  if (!have_v) {
-#ifdef PB200_STREAM_MATVEC
-    if (streamed) At_times_stream(A, W, W.y, W.w);
-    else
-#endif
-      At_times(A, W.y, W.w);
-  }
+  if (!have_v) At_times(A, W.y, W.w);
   double ss = 0.0;
   for (int j = tid; j < n; j += NT) {
     double v = have_v ? W.t[j] : W.w[j], xj = W.x[j], zj = W.z[j], cj = (j == tid) ? c_first : W.c[j];
@@ -553,11 +536,7 @@ static __device__ __forceinline__ void prepare_rhs(const Matrix& A, Work& W, dou
   }
   norms = sqrt(block_sum(ss, W.red));          // (syncs: t, d, q visible)
   // S <- A x ; RHS <- A q
-#ifdef PB200_STREAM_MATVEC
-  if (streamed) A_times2_stream(A, W, W.x, W.w, W.S, W.RHS, W.g1, W.g2);
-  else
-#endif
-    A_times2(A, W.x, W.w, W.S, W.RHS, W.g1, W.g2);
+  A_times2(A, W.x, W.w, W.S, W.RHS, W.g1, W.g2);
   double rr = 0.0;
   for (int i = tid; i < m; i += NT) {
     double rho = W.b[i] - W.S[i];
@@ -573,11 +552,7 @@ template <bool VS>
 static __device__ __forceinline__ void step(const Matrix& A, Work& W, double mu, double r) {
   const int m = A.m, n = A.n, tid = threadIdx.x;
   const double c_first = (tid < n) ? W.c[tid] : 0.0;
-#ifdef PB200_STREAM_MATVEC
-  if (VS && !A.sparse) At_times_stream(A, W, W.dy, W.w);
-  else
-#endif
-    At_times(A, W.dy, W.w);
+  At_times(A, W.dy, W.w);
   double th = 0.0;
   for (int j = tid; j < n; j += NT) {
     double xj = W.x[j], zj = W.z[j];

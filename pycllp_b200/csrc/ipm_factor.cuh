@@ -431,263 +431,6 @@ static __device__ __forceinline__ void factor_ldl_fast(int m, Work& W, double be
 }
 
 // ---------------------------------------------------------------------------------------
-// factor_ldl_pipe: the same factorisation with ONE PANEL OF LOOK-AHEAD, for L in shared memory
-// and m <= 8*35 (every row tile of a panel fits one of 36 warp slots).
-//
-// The update of panel p+1 is split into the part that only needs finished columns (k < j0,
-// "OLD") and the contribution of panel p itself (8 columns, "NEW"):
-//   S1  warp 0 eliminates the diagonal block of panel p (diag_block, the serial bottleneck)
-//       WHILE the twelve warps of sub-partitions 1-3 run the OLD DMMA loops of panel p+1 and
-//       keep the accumulators in registers;                                   __syncthreads
-//   S2  all threads: rows below the block are solved against it (one row per thread), the rhs
-//       row rides along (forward substitution);                                __syncthreads
-//   S3  the same twelve warps add the NEW part (two DMMAs per tile), subtract from M and store
-//       the updated panel p+1; warps 0,4,8,12 prepare D_k L(rows of block p+2, k) for the next
-//       OLD loops;                                                             __syncthreads
-// so the long DMMA loops, the multiplier table and the diagonal-tile update are off the
-// critical path, which is  diag_block + row solves + three barriers  per panel.
-// Purely speculative (theta clamp assumed inactive, |pivot| > delta decided on high words):
-// returns true if any panel could not be proven equivalent to the sequential rule; the caller
-// then restores M and runs factor_ldl_fast, which redoes offending panels exactly.
-// ---------------------------------------------------------------------------------------
-__device__ __forceinline__ void pipe_old_unit(const double* __restrict__ L, const double* __restrict__ PB,
-                                              const double* __restrict__ Sf, int m, int K, int tg,
-                                              int g, int rs, bool is_rhs, double& c0, double& c1) {
-  // four split-K chains; k-step ks covers columns 4ks..4ks+3
-  double e0 = 0.0, e1 = 0.0, f0 = 0.0, f1 = 0.0, h0 = 0.0, h1 = 0.0;
-  c0 = c1 = 0.0;
-  const int nks = K >> 2;
-  int k = tg;
-  const double* pa = L + coff(k, m) + rs;
-  int d = 4 * m - 8 - 4 * tg;
-  const double* pb = PB + tg * NB + g;
-  int ks = 0;
-  for (; ks + 4 <= nks; ks += 4) {
-    double a0, a1, a2, a3;
-    if (is_rhs) {
-      const bool on = (g == 0);
-      a0 = on ? Sf[k] : 0.0; a1 = on ? Sf[k + 4] : 0.0; a2 = on ? Sf[k + 8] : 0.0; a3 = on ? Sf[k + 12] : 0.0;
-    } else {
-      a0 = pa[0]; pa += d; d -= 16;
-      a1 = pa[0]; pa += d; d -= 16;
-      a2 = pa[0]; pa += d; d -= 16;
-      a3 = pa[0]; pa += d; d -= 16;
-    }
-    const double b0 = pb[0], b1 = pb[4 * NB], b2 = pb[8 * NB], b3 = pb[12 * NB];
-    pb += 16 * NB;
-    k += 16;
-    dmma884(c0, c1, a0, b0);
-    dmma884(e0, e1, a1, b1);
-    dmma884(f0, f1, a2, b2);
-    dmma884(h0, h1, a3, b3);
-  }
-  for (; ks < nks; ks++) {
-    double a0;
-    if (is_rhs) a0 = (g == 0) ? Sf[k] : 0.0;
-    else { a0 = pa[0]; pa += d; d -= 16; }
-    const double b0 = pb[0];
-    pb += 4 * NB;
-    k += 4;
-    dmma884(c0, c1, a0, b0);
-  }
-  c0 = (c0 + e0) + (f0 + h0);
-  c1 = (c1 + e1) + (f1 + h1);
-}
-
-static __device__ __forceinline__ bool factor_ldl_pipe(int m, Work& W, double beta, double delta,
-                                                       const double* __restrict__ rhs,
-                                                       double* __restrict__ Sf) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = warp_id();
-  const int g = lane >> 2, tg = lane & 3;
-  double* __restrict__ L = W.L;
-  double* __restrict__ D = W.D;
-  double* PB0 = W.P;
-  double* PB1 = W.P + (size_t)m * NB;
-  double* Wm = W.red + RED_W;
-  double* D1 = W.red + RED_D1;
-  double* rinv = W.red + RED_RINV;
-  double* crhs = W.red + RED_CRHS;
-  int* thbuf = reinterpret_cast<int*>(W.red + RED_TH);
-  const double inv_beta2 = 1.0 / (beta * beta);
-  const int np = (m + 7) >> 3;
-  const int wsub = warp & 3;
-  const bool isK = wsub != 0;
-  const int widx = (warp >> 2) * 3 + wsub - 1;     // 0..11 for the DMMA warps
-  bool bad = false;
-
-  if (tid < 8) crhs[tid] = (tid < m) ? rhs[tid] : 0.0;
-  if (tid < 16) thbuf[tid] = 0;
-  __syncthreads();
-
-  for (int p = 0; p < np; p++) {
-    const int j0 = 8 * p;
-    const int nb = min(NB, m - j0);
-    int* th = thbuf + (p & 1) * 8;
-    const bool more = p + 1 < np;
-    const int j1 = j0 + 8;
-    const int nt1 = more ? ((m - j1 + 7) >> 3) : 0;   // row tiles of panel p+1 (unit nt1 = rhs row)
-    double acc[3][2];
-#pragma unroll
-    for (int s = 0; s < 3; s++) acc[s][0] = acc[s][1] = 0.0;
-
-    // ---- S1 ----
-    long long tq = phase_begin(W);
-    if (warp == 0) {
-      const long long tb = phase_begin(W);
-      diag_block(m, j0, nb, W, delta, th, Wm, D1, rinv);
-      phase_end(W, 9, tb);
-    } else if (isK && more && j0 > 0) {
-      const long long tw = W.prof ? clock64() : 0;
-      const double* PB = ((p + 1) & 1) ? PB1 : PB0;
-      // units widx and widx+12 share their B fragments (two tiles per k-step), widx+24 alone;
-      // the rhs row (unit nt1) goes through the generic loop
-      const int u0 = widx, u1 = widx + 12, u2 = widx + 24;
-      const int r0 = j1 + 8 * u0 + g, r1 = j1 + 8 * u1 + g, r2 = j1 + 8 * u2 + g;
-      const int s0 = (r0 < m) ? r0 : j1, s1 = (r1 < m) ? r1 : j1, s2 = (r2 < m) ? r2 : j1;
-      if (u1 < nt1) {
-        panel_update_tiles<true>(L, PB, m, j0, tg, g, s0, s1 - s0, acc[0][0], acc[0][1], acc[1][0], acc[1][1]);
-      } else {
-        double d0, d1;
-        if (u0 < nt1) panel_update_tiles<false>(L, PB, m, j0, tg, g, s0, 0, acc[0][0], acc[0][1], d0, d1);
-        else if (u0 == nt1) pipe_old_unit(L, PB, Sf, m, j0, tg, g, j1, true, acc[0][0], acc[0][1]);
-        if (u1 == nt1) pipe_old_unit(L, PB, Sf, m, j0, tg, g, j1, true, acc[1][0], acc[1][1]);
-      }
-      if (u2 <= nt1) {
-        double d0, d1;
-        if (u2 < nt1) panel_update_tiles<false>(L, PB, m, j0, tg, g, s2, 0, acc[2][0], acc[2][1], d0, d1);
-        else pipe_old_unit(L, PB, Sf, m, j0, tg, g, j1, true, acc[2][0], acc[2][1]);
-      }
-      if (W.prof) {
-        const unsigned long long dt = (unsigned long long)(clock64() - tw);
-        if (tid == 32) reinterpret_cast<unsigned long long*>(W.red + RED_PROF)[13] += dt;
-      }
-    }
-    __syncthreads();
-    phase_end(W, 8, tq);
-    tq = phase_begin(W);
-
-    // ---- S2: rows below the diagonal block (+ the rhs row), one thread each ----
-    {
-      const int R = m - j0;
-      const int nbelow = (R > 8) ? R - 8 : 0;
-      const int nrows = nbelow + 1;
-      int hmax[8];
-#pragma unroll
-      for (int jj = 0; jj < 8; jj++) hmax[jj] = 0;
-      if (tid >= NT - 8 && tid - (NT - 8) < nb) D[j0 + tid - (NT - 8)] = D1[tid - (NT - 8)];
-      int cb[8];
-#pragma unroll
-      for (int j = 0; j < 8; j++) cb[j] = coff(min(j0 + j, m - 1), m);
-      for (int t = tid; t < nrows; t += NT) {
-        const bool is_rhs = (t == nbelow);
-        const int row = is_rhs ? m - 1 : j0 + 8 + t;
-        double c[8];
-#pragma unroll
-        for (int jj = 0; jj < 8; jj++) {
-          double cv = (jj < nb) ? L[cb[jj] + row] : 0.0;
-          if (is_rhs) cv = (jj < nb) ? crhs[jj] : 0.0;
-          c[jj] = cv;
-        }
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-          if (!is_rhs) hmax[k] = max(hmax[k], dbl_hi(c[k]) & 0x7fffffff);
-          const double lk = c[k] * rinv[k];
-#pragma unroll
-          for (int jj = k + 1; jj < 8; jj++) c[jj] -= lk * Wm[jj * 8 + k];
-          c[k] = lk;
-        }
-#pragma unroll
-        for (int jj = 0; jj < 8; jj++) {
-          if (jj < nb) {
-            if (is_rhs) Sf[j0 + jj] = c[jj];
-            else L[cb[jj] + row] = c[jj];
-          }
-        }
-      }
-      int hm = 0;
-#pragma unroll
-      for (int jj = 0; jj < 8; jj++) {
-        const int r = __reduce_max_sync(0xffffffffu, hmax[jj]);
-        if (lane == jj) hm = r;
-      }
-      if (lane < 8 && hm > 0) atomicMax(&th[lane], hm);
-    }
-    __syncthreads();
-    phase_end(W, 10, tq);
-    tq = phase_begin(W);
-
-    // ---- S3 ----
-    {
-      const int jj = lane & 7;
-      const double tub = __hiloint2double(th[jj] + 1, 0);
-      const bool mine = (jj < nb) && !(tub * tub * inv_beta2 * 1.0000001 <= D1[jj]);
-      bad |= __any_sync(0xffffffffu, mine);
-    }
-    if (more) {
-      const int nb1 = min(NB, m - j1);
-      if (isK) {
-        // NEW part: columns j0..j0+7 of this panel; B(k, n) = D_k L(j1+n, k)
-        const int ka = j0 + tg, kb = j0 + 4 + tg;
-        const int ca = coff(ka, m), cbk = coff(kb, m);
-        const bool nok = (j1 + g) < m;
-        const double ba = nok ? D1[tg] * L[ca + j1 + g] : 0.0;
-        const double bb = nok ? D1[4 + tg] * L[cbk + j1 + g] : 0.0;
-#pragma unroll
-        for (int s = 0; s < 3; s++) {
-          const int u = widx + 12 * s;
-          if (u <= nt1) {
-            const bool is_rhs = (u == nt1);
-            const int row = j1 + 8 * u + g;
-            const bool ok = !is_rhs && row < m;
-            double a0, a1;
-            if (is_rhs) { a0 = (g == 0) ? Sf[ka] : 0.0; a1 = (g == 0) ? Sf[kb] : 0.0; }
-            else { const int rs = ok ? row : j1; a0 = L[ca + rs]; a1 = L[cbk + rs]; }
-            dmma884(acc[s][0], acc[s][1], a0, ba);
-            dmma884(acc[s][0], acc[s][1], a1, bb);
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-              const int col = 2 * tg + h;
-              if (col < nb1) {
-                if (is_rhs) { if (g == 0) crhs[col] = rhs[j1 + col] - acc[s][h]; }
-                else if (ok && row >= j1 + col) L[coff(j1 + col, m) + row] -= acc[s][h];
-              }
-            }
-          }
-        }
-      }
-      if (tid < 8) thbuf[((p + 1) & 1) * 8 + tid] = 0;
-      // multipliers of the OLD loops of panel p+2: D_k L(j0+16+jj, k), k < j0+8 (rows of block
-      // p+2 were finished in S2): a few entries per thread, warps 0/4/8/12 start right away
-      if (p + 2 < np) {
-        const int j2 = j0 + 16;
-        const int nb2 = min(NB, m - j2);
-        double* PBn = (p & 1) ? PB1 : PB0;
-        // sub-partition-0 warps take the first half of the table, the DMMA warps (after their
-        // two DMMAs per tile) the second half
-        const int total = j1 * NB;
-        const int half = (total / 2) & ~7;
-        if (!isK) {
-          const int t4 = (warp >> 2) * 32 + lane;            // 0..127
-          for (int e = t4; e < half; e += 128) {
-            const int k = e >> 3, jj = e & 7;
-            PBn[e] = (jj < nb2) ? L[coff(k, m) + j2 + jj] * D[k] : 0.0;
-          }
-        } else {
-          const int t12 = widx * 32 + lane;                  // 0..383
-          for (int e = half + t12; e < total; e += 384) {
-            const int k = e >> 3, jj = e & 7;
-            PBn[e] = (jj < nb2) ? L[coff(k, m) + j2 + jj] * D[k] : 0.0;
-          }
-        }
-      }
-    }
-    __syncthreads();
-    phase_end(W, 11, tq);
-  }
-  return bad;
-}
-
-// ---------------------------------------------------------------------------------------
 // factor_ldl_ahead: the same factorisation with the SERIAL CHAIN ON ITS OWN WARP.
 //
 // The chain  diag_block(p) -> rows of block p+1 solved against it -> diagonal tile p+1 updated
@@ -705,8 +448,8 @@ static __device__ __forceinline__ bool factor_ldl_pipe(int m, Work& W, double be
 //                      free of DMMAs, see profiles/fp64_latency_r01.txt) ; [E3: arrive]
 // so every panel q receives the columns k < 8(q-1) two panels early (step 3 of panel q-2) and
 // the eight columns of panel q-1 one panel early (step 1 of panel q-1 / warp 0).
-// The right-hand side rides along as an extra row kept in Sf (in place).  Speculative like
-// factor_ldl_pipe: returns true if some panel could not be proven equivalent to the sequential
+// The right-hand side rides along as an extra row kept in Sf (in place).  Speculative:
+// returns true if some panel could not be proven equivalent to the sequential
 // rule (theta clamp active, huge or tied pivot); the caller then redoes the factorisation.
 // Requires L in shared memory and m <= 8*35.
 // ---------------------------------------------------------------------------------------

@@ -38,8 +38,8 @@ static __device__ __forceinline__ void carve(const Matrix& A, const Scratch& sc,
   if constexpr (LS) W.L = smem + o;
   else W.L = slot + sc.off_L;
   if constexpr (VS) {
-    // the streamed A_times2 needs its gather buffers outside the stage ring: the factor's
-    // storage is dead while the right-hand side is prepared; without it, 2 ldd more doubles
+    // gather buffers of A_times2: the factor's storage is dead while the right-hand side is
+    // prepared; without it in shared memory, 2 ldd more doubles after the vectors
     W.g1 = smem + o;
     W.g2 = W.g1 + ldd1;
   }

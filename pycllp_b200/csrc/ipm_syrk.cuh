@@ -251,170 +251,6 @@ static __device__ __forceinline__ void form_M_dense_tma(const Matrix& A, Work& W
 }
 
 
-// ---------------------------------------------------------------------------------------
-// Streamed mat-vecs.  Read straight from L2 the three products with A per Newton step and the
-// residual with M were latency-bound (20-35 B/cycle per SM); streamed through the same TMA ring
-// as the SYRK operand the loads are bulk copies with deep memory-level parallelism and the
-// dot products read shared memory.  All 16 warps run the ring protocol for every chunk:
-// wait on the stage's mbarrier, work, count themselves out; the last one refills the stage.
-//   src_of(c) -> global address of chunk c, bytes_of(c) -> its size (multiple of 16), body(S, c).
-// ---------------------------------------------------------------------------------------
-template <class SrcF, class BytesF, class BodyF>
-__device__ __forceinline__ void stream_chunks(Work& W, int total, int stage_doubles, SrcF src_of,
-                                              BytesF bytes_of, BodyF body) {
-  const int tid = threadIdx.x, lane = tid & 31;
-  uint64_t* full = reinterpret_cast<uint64_t*>(W.red + RED_MBAR);
-  int* done = reinterpret_cast<int*>(full + SY_STAGES);
-  const int g0 = W.ring_g;
-  __syncthreads();
-  if (tid == 0) {
-    // the stages were last touched (and the source possibly written) through the generic proxy
-    asm volatile("fence.proxy.async;" ::: "memory");
-    for (int c = 0; c < SY_STAGES && c < total; c++) {
-      const int st = (g0 + c) % SY_STAGES;
-      mbar_expect_tx(&full[st], bytes_of(c));
-      tma_load_1d(W.P + st * stage_doubles, src_of(c), bytes_of(c), &full[st]);
-    }
-  }
-  for (int c = 0; c < total; c++) {
-    const int st = (g0 + c) % SY_STAGES;
-    mbar_wait(&full[st], ((g0 + c) / SY_STAGES) & 1);
-    body(W.P + st * stage_doubles, c);
-    __syncwarp();
-    if (lane == 0) {
-      if (atom_add_acq_rel(&done[st], 1) == NWARP - 1) {
-        done[st] = 0;
-        const int cn = c + SY_STAGES;
-        if (cn < total) {
-          mbar_expect_tx(&full[st], bytes_of(cn));
-          tma_load_1d(W.P + st * stage_doubles, src_of(cn), bytes_of(cn), &full[st]);
-        }
-      }
-    }
-  }
-  W.ring_g = g0 + total;
-  __syncthreads();
-}
-
-// Eight dot products per chunk: chunk c holds vectors 8c..8c+7, `ld` apart, `len` long; warps
-// 0-7 take the even chunks (one vector each), warps 8-15 the odd ones, so two chunks are in
-// work at any time.  emit(index, value) is called by lane 0 of the warp that owns the vector.
-// pre(index) is evaluated before the dot product (e.g. a global table look-up whose latency
-// should not follow the reduction) and handed to emit.
-template <class PreF, class EmitF>
-__device__ __forceinline__ void stream_dots(Work& W, const double* __restrict__ base, int nvec, int ld,
-                                            int len, const double* __restrict__ vec, PreF pre, EmitF emit) {
-  const int lane = threadIdx.x & 31, warp = warp_id();
-  const int total = (nvec + 7) >> 3;
-  const int stage_doubles = SY_KC * ld;
-  auto src_of = [&](int c) { return base + (size_t)c * stage_doubles; };
-  auto bytes_of = [&](int c) {
-    const int nv = min(8, nvec - 8 * c);
-    return (uint32_t)(((size_t)nv * ld * sizeof(double) + 15) & ~(size_t)15);
-  };
-  stream_chunks(W, total, stage_doubles, src_of, bytes_of, [&](const double* __restrict__ S, int c) {
-    if ((c & 1) == (warp >> 3)) {
-      const int k = 8 * c + (warp & 7);
-      if (k < nvec) {
-        const double* __restrict__ col = S + (warp & 7) * ld;
-        const int tok = pre(k);
-        double a0 = 0.0, a1 = 0.0;
-        int i = lane;
-        for (; i + 32 < len; i += 64) {
-          a0 += col[i] * vec[i];
-          a1 += col[i + 32] * vec[i + 32];
-        }
-        if (i < len) a0 += col[i] * vec[i];
-        const double t = warp_sum(a0 + a1);
-        if (lane == 0) emit(k, tok, t);
-      }
-    }
-  });
-}
-
-// out = A' u on the packed operand (columns of A with >= 2 non-zeros), streamed; singleton
-// columns are one multiply.  Ends with __syncthreads().
-__device__ __forceinline__ void At_times_stream(const Matrix& A, Work& W, const double* __restrict__ u,
-                                                double* __restrict__ out) {
-  const int n = A.n, jt = threadIdx.x;
-  int r0 = -2;
-  double cv0 = 0.0;
-  if (jt < n) { r0 = A.colrow[jt]; cv0 = A.colval[jt]; }
-#ifdef PB200_AT_NOPRE
-  stream_dots(W, A.sy_A, A.nd, A.sy_ldm, A.m, u, [](int) { return 0; },
-              [&](int k, int, double t) { out[A.dcols[k]] = t; });
-#else
-  stream_dots(W, A.sy_A, A.nd, A.sy_ldm, A.m, u, [&](int k) { return A.dcols[k]; },
-              [&](int, int j, double t) { out[j] = t; });
-#endif
-  if (jt < n && r0 != -2) out[jt] = (r0 >= 0) ? cv0 * u[r0] : 0.0;
-  for (int j = jt + NT; j < n; j += NT) {
-    const int r = A.colrow[j];
-    if (r != -2) out[j] = (r >= 0) ? A.colval[j] * u[r] : 0.0;
-  }
-  __syncthreads();
-}
-
-// o1 = A u1, o2 = A u2, streamed over the k-major packed operand; two threads per row (each
-// takes four of the eight columns of a chunk).  Requires m <= NT/2.  g1/g2: 2 x ldd doubles
-// outside the stage ring.  Ends with __syncthreads().
-__device__ __forceinline__ void A_times2_stream(const Matrix& A, Work& W, const double* __restrict__ u1,
-                                                const double* __restrict__ u2, double* __restrict__ o1,
-                                                double* __restrict__ o2, double* __restrict__ g1,
-                                                double* __restrict__ g2) {
-  const int m = A.m, ldd = A.ldd, ldm = A.sy_ldm, tid = threadIdx.x;
-  for (int k = tid; k < ldd; k += NT) {
-    const bool ok = k < A.nd;
-    const int j = ok ? A.dcols[k] : 0;
-    g1[k] = ok ? u1[j] : 0.0;
-    g2[k] = ok ? u2[j] : 0.0;
-  }
-  // singleton (slack) columns: one thread per row, added at the end
-  double s1 = 0.0, s2 = 0.0;
-  const int row = tid >> 1, half = tid & 1;
-  if (half == 0 && row < m) {
-    for (int e = A.sing_ptr[row]; e < A.sing_ptr[row + 1]; e++) {
-      const double a = A.sing_a[e];
-      const int j = A.sing_col[e];
-      s1 += a * u1[j];
-      s2 += a * u2[j];
-    }
-  }
-  const int total = ldd / SY_KC;
-  const int stage_doubles = SY_KC * ldm;
-  const uint32_t bytes = (uint32_t)(stage_doubles * sizeof(double));
-  double a1 = 0.0, a2 = 0.0;
-  stream_chunks(W, total, stage_doubles, [&](int c) { return A.sy_A + (size_t)c * stage_doubles; },
-                [&](int) { return bytes; }, [&](const double* __restrict__ S, int c) {
-                  if (row < m) {
-                    const double* __restrict__ p = S + (4 * half) * ldm + row;
-                    const double* __restrict__ x = g1 + c * SY_KC + 4 * half;
-                    const double* __restrict__ q = g2 + c * SY_KC + 4 * half;
-#pragma unroll
-                    for (int kk = 0; kk < 4; kk++) {
-                      const double a = p[kk * ldm];
-                      a1 += a * x[kk];
-                      a2 += a * q[kk];
-                    }
-                  }
-                });
-  a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
-  a2 += __shfl_xor_sync(0xffffffffu, a2, 1);
-  if (half == 0 && row < m) { o1[row] = a1 + s1; o2[row] = a2 + s2; }
-  __syncthreads();
-}
-
-// S = RHS - M dy ; returns max |S|, M (row-major, the block's scratch slot) streamed.
-__device__ __forceinline__ double residual_stream(int m, Work& W) {
-  double mx = 0.0;
-  stream_dots(W, W.M, m, m, m, W.dy, [](int) { return 0; }, [&](int i, int, double t) {
-    const double r = W.RHS[i] - t;
-    W.S[i] = r;
-    mx = fmax(mx, fabs(r));
-  });
-  return block_max(mx, W.red);
-}
-
 // Out-of-line entry: the SYRK loop needs ~100 registers of its own (12 accumulator tiles,
 // prefetched fragments).  Inlined into the persistent kernel its register allocation is at the
 // mercy of everything that is live around it (seen: the fragment loads collapse onto one
