@@ -67,3 +67,49 @@ def test_allgather_results_gloo(world, N):
     assert sorted(r[0] for r in results) == list(range(world))
     assert all(r[1] for r in results)
     assert all(r[2][0] == world for r in results)
+
+
+def _nccl_worker(rank, world, port, q):
+    """One rank = one GPU: solve this rank's slice through the plugin API and all-gather over NCCL."""
+    import torch
+    import torch.distributed as dist
+    from pycllp_b200.lp import StandardLP
+    from pycllp_b200.problems import random_problem
+    from pycllp_b200.solvers import solver_registry
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world)
+    try:
+        lp = StandardLP(*random_problem(50, 50, 0.1, 37)).to_equality_form()     # ragged over 2 ranks
+        sharded = solver_registry["cl_dense_primal_normal"](rank, group=True)
+        lp.init(sharded)
+        lp.solve(sharded)
+        whole = solver_registry["cl_dense_primal_normal"](rank)
+        lp.init(whole)
+        lp.solve(whole)
+        ok = all(np.array_equal(getattr(sharded, k), getattr(whole, k)) for k in ("x", "y", "z", "status", "iterations"))
+        q.put((rank, ok, int(sharded.x.shape[0])))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_sharded_solve_gathers_over_nccl():
+    """Two GPUs, one process each: the sharded solve + NCCL all-gather gives every rank exactly
+    what a single GPU computes for the whole batch (skipped on a one-GPU box)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=300) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(r[0] for r in results) == [0, 1]
+    assert all(r[1] for r in results) and all(r[2] == 37 for r in results)
