@@ -73,6 +73,10 @@ static __device__ __forceinline__ void ipm_solve_one(const Matrix& A, const Batc
   int stat = 5;                                   // primal_normal.cl:225
   double normr0 = INFINITY, norms0 = INFINITY;    // HUGE_VALF/10, :227-228
   int iter;
+  // v = A'y is carried over from the previous step (one pass over A less) for the first 64
+  // iterations -- every LP that converges is done long before -- and recomputed from y like the
+  // reference does afterwards, which bounds the drift on the long diverging runs of infeasible LPs
+  bool carry_v = false;
   for (iter = 0; iter < p.max_iter; iter++) {
     double g = 0.0;
     for (int j = tid; j < n; j += NT) g += W.z[j] * W.x[j];
@@ -80,7 +84,8 @@ static __device__ __forceinline__ void ipm_solve_one(const Matrix& A, const Batc
     const double mu = p.delta * gamma / (double)(n + m);          // :272
     double normr, norms;
     long long t0 = phase_begin(W);
-    prepare_rhs<VS>(A, W, mu, normr, norms, iter > 0);
+    prepare_rhs<VS>(A, W, mu, normr, norms, carry_v);
+    carry_v = iter + 1 < 64;
     phase_end(W, 0, t0);
     if (normr < p.eps && norms < p.eps && gamma < p.eps) { stat = 0; break; }   // :256-259
     if (normr > 10 * normr0 && normr > p.eps) { stat = 2; break; }              // :261-264

@@ -1,7 +1,9 @@
 """Ad-hoc GPU check: engine vs oracle on small configs + a first timing. Not a test."""
 import sys, time, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
+from pycllp_b200 import _cabi
+if os.environ.get("PB200_LIB"): _cabi.LIB_PATH = os.environ["PB200_LIB"]
 from pycllp_b200._cabi import Engine
 from pycllp_b200.problems import random_equality_arrays, sparse_equality_arrays
 from oracle.bindings import Oracle
