@@ -247,9 +247,22 @@ static __device__ __forceinline__ void factor_ldl_fast(int m, Work& W, double be
     int* th = thbuf + parity * 8;
     long long tq = phase_begin(W);
     // P[k][jj] = D_k L(j0+jj, k)
-    for (int e = tid; e < j0 * NB; e += NT) {
-      const int k = e >> 3, jj = e & 7;
-      P[e] = (jj < nb) ? L[coff(k, m) + j0 + jj] * D[k] : 0.0;
+    // (four entries per thread and round: the loads are issued together -- the compiler cannot move a
+    // load of L across a store to P on its own, and with L in global memory every round would be
+    // one exposed L2 round trip)
+    for (int e0 = tid; e0 < j0 * NB; e0 += 4 * NT) {
+      double v[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const int e = e0 + q * NT;
+        const int k = min(e, j0 * NB - 1) >> 3, jj = e & 7;
+        v[q] = (jj < nb) ? L[coff(k, m) + j0 + jj] * D[k] : 0.0;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const int e = e0 + q * NT;
+        if (e < j0 * NB) P[e] = v[q];
+      }
     }
     if (tid < 8) th[tid] = 0;
     __syncthreads();
@@ -306,14 +319,21 @@ static __device__ __forceinline__ void factor_ldl_fast(int m, Work& W, double be
         double c0, c1, u0, u1;
         if (two) panel_update_tiles<true>(L, P, m, j0, tg, g, ra, rb - ra, c0, c1, u0, u1);
         else panel_update_tiles<false>(L, P, m, j0, tg, g, ra, 0, c0, c1, u0, u1);
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-          const int col = 2 * tg + h;
-          if (col < nb) {
-            const int cb = coff(j0 + col, m);
-            if (oka) L[cb + rowa] -= (h ? c1 : c0);
-            if (okb) L[cb + rowb] -= (h ? u1 : u0);
-          }
+        // L -= acc: all four loads first, then the stores (written as four read-modify-writes the
+        // compiler keeps them in order, and with L in global memory that is four L2 round trips
+        // per tile pair -- 7 % of all warp samples at config 5)
+        {
+          const int cA = coff(min(j0 + 2 * tg, m - 1), m), cB = coff(min(j0 + 2 * tg + 1, m - 1), m);
+          const bool h0 = 2 * tg < nb, h1 = 2 * tg + 1 < nb;
+          double* pa0 = L + cA + (oka ? rowa : j0);
+          double* pa1 = L + cB + (oka ? rowa : j0);
+          double* pb0 = L + cA + (okb ? rowb : j0);
+          double* pb1 = L + cB + (okb ? rowb : j0);
+          const double va0 = *pa0, va1 = *pa1, vb0 = *pb0, vb1 = *pb1;
+          if (oka && h0) *pa0 = va0 - c0;
+          if (oka && h1) *pa1 = va1 - c1;
+          if (okb && h0) *pb0 = vb0 - u0;
+          if (okb && h1) *pb1 = vb1 - u1;
         }
       }
       if (W.prof) {
