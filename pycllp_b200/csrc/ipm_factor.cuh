@@ -381,13 +381,15 @@ static __device__ __forceinline__ void factor_ldl_fast(int m, Work& W, double be
         const bool is_rhs = (t == nbelow);
         const int row = is_rhs ? m - 1 : j0 + 8 + t;
         double c[8];
+        // (all eight loads before the first store: eight L2 round trips in parallel, not in series)
 #pragma unroll
         for (int jj = 0; jj < 8; jj++) {
           double cv = (jj < nb) ? L[cb[jj] + row] : 0.0;
           if (is_rhs) cv = (jj < nb) ? crhs[jj] : 0.0;
-          P[jj * nthr_rows + t] = cv;                          // kept for the exact redo (conflict-free)
           c[jj] = cv;
         }
+#pragma unroll
+        for (int jj = 0; jj < 8; jj++) P[jj * nthr_rows + t] = c[jj];   // kept for the exact redo (conflict-free)
         // right-looking inside the row: l_k = c_k / D_k, then c_jj -= l_k * (D_k L11[jj][k])
 #pragma unroll
         for (int k = 0; k < 8; k++) {
