@@ -473,9 +473,21 @@ static __device__ __forceinline__ void solve_normal(const Matrix& A, Work& W, co
   const double beta = sqrt(block_max(bmax, W.red));
   // the factorisation works in place on the packed lower triangle (the dense SYRK wrote it)
   if (A.sparse || !VS) {
-    for (int e = tid; e < m * m; e += NT) {
-      const int j = e / m, i = e - j * m;
-      if (i >= j) W.L[cidx(i, j, m)] = W.M[(size_t)j * m + i];
+    // (four loads in flight per thread: written element by element, the copy is one memory round
+    // trip per element, since the compiler may not move a load of M across a store to L)
+    for (int e0 = tid; e0 < m * m; e0 += 4 * NT) {
+      double v[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const int e = min(e0 + q * NT, m * m - 1);
+        v[q] = W.M[e];                                   // M[j][i], e = j m + i
+      }
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const int e = e0 + q * NT;
+        const int j = e / m, i = e - j * m;
+        if (e < m * m && i >= j) W.L[cidx(i, j, m)] = v[q];
+      }
     }
   }
   for (int i = tid; i < m; i += NT) W.dy[i] = 0.0;

@@ -101,3 +101,16 @@ if "prof5" in which:
     print("cfg5 N=%d %.3fs (%.0f solves/s); phase cycles per Newton step:" % (N, dt, N / dt))
     for k, v in prof.items():
         print("  %-14s %10.0f cyc/step  %5.1f%%" % (k, v / steps, 100.0 * v / tot))
+
+if "prof4" in which:
+    N = int(os.environ.get("N4", "148"))
+    A, b, c = sparse_equality_arrays(2000, 3000, 0.01, N, seed=0)
+    eng.setup_sparse(A, N)
+    eng.phase_profile(True)
+    t = time.time(); res = eng.solve_host(b, c); dt = time.time() - t
+    prof = eng.phase_profile(False)
+    steps = res["iters"].sum()
+    tot = sum(v for k, v in prof.items() if k in ("rhs_norms", "form_M", "factor", "tri_solve", "residual", "step", "f_copy"))
+    print("cfg4 N=%d %.3fs (%.1f solves/s); phase cycles per Newton step:" % (N, dt, N / dt))
+    for k, v in prof.items():
+        print("  %-14s %10.0f cyc/step  %5.1f%%" % (k, v / steps, 100.0 * v / tot))
