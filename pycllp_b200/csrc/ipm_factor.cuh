@@ -530,11 +530,12 @@ static __device__ __forceinline__ void block_row(int m, int j0, int nb, Work& W,
     dmma884(d0, d1, L[coff(j0 + tg, m) + ra], Wp[tg * PBS + g]);
     dmma884(d0, d1, L[coff(min(j0 + 4 + tg, m - 1), m) + ra], Wp[(4 + tg) * PBS + g]);
     const int r2 = j1 + g;
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-      const int col = 2 * tg + h;
-      if (r2 < m && col <= g) L[coff(j1 + col, m) + r2] -= (h ? d1 : d0);
-    }
+    const bool w0 = r2 < m && 2 * tg <= g, w1 = r2 < m && 2 * tg + 1 <= g;
+    double* q0 = L + coff(min(j1 + 2 * tg, m - 1), m) + (r2 < m ? r2 : m - 1);
+    double* q1 = L + coff(min(j1 + 2 * tg + 1, m - 1), m) + (r2 < m ? r2 : m - 1);
+    const double v0 = *q0, v1 = *q1;               // (both loads before the stores)
+    if (w0) *q0 = v0 - d0;
+    if (w1) *q1 = v1 - d1;
   }
   __syncwarp();
 }
@@ -576,16 +577,20 @@ __device__ __forceinline__ void old_update16(const double* __restrict__ L, const
 // panel jc (nbc columns), rows ra+2g / ra+2g+1  -=  the accumulators of old_update16
 __device__ __forceinline__ void sub_unit16(double* __restrict__ L, int m, int jc, int nbc, int ra, int g,
                                            int tg, double c0, double c1, double u0, double u1) {
+  // (the four loads first, then the four stores: as four read-modify-writes the compiler keeps them
+  // in order -- four shared-memory round trips in series on a phase that is a few hundred cycles long)
   const int rowA = ra + 2 * g, rowB = rowA + 1;
-#pragma unroll
-  for (int h = 0; h < 2; h++) {
-    const int col = 2 * tg + h;
-    if (col < nbc) {
-      double* dst = L + coff(jc + col, m);
-      if (rowA < m && rowA >= jc + col) dst[rowA] -= (h ? c1 : c0);
-      if (rowB < m && rowB >= jc + col) dst[rowB] -= (h ? u1 : u0);
-    }
-  }
+  const int col0 = 2 * tg, col1 = col0 + 1;
+  double* d0 = L + coff(min(jc + col0, m - 1), m);
+  double* d1 = L + coff(min(jc + col1, m - 1), m);
+  const bool a0 = col0 < nbc && rowA < m && rowA >= jc + col0, b0 = col0 < nbc && rowB < m && rowB >= jc + col0;
+  const bool a1 = col1 < nbc && rowA < m && rowA >= jc + col1, b1 = col1 < nbc && rowB < m && rowB >= jc + col1;
+  const int sA = rowA < m ? rowA : m - 1, sB = rowB < m ? rowB : m - 1;   // (always valid addresses)
+  const double vA0 = d0[sA], vB0 = d0[sB], vA1 = d1[sA], vB1 = d1[sB];
+  if (a0) d0[rowA] = vA0 - c0;
+  if (b0) d0[rowB] = vB0 - u0;
+  if (a1) d1[rowA] = vA1 - c1;
+  if (b1) d1[rowB] = vB1 - u1;
 }
 
 // Step 1a of factor_ldl_ahead for one row (two threads per row do the same work, thread
@@ -610,14 +615,21 @@ __device__ __forceinline__ void step1_solve(double* __restrict__ L, int m, int j
     if (!FULL) cb[jj] = coff(min(j0 + jj, m - 1), m);
     c[jj] = (FULL || jj < nb) ? Lr[cb[jj]] : 0.0;
   }
+  double un[8];                                 // unscaled entries D_k l_k (table rows of block p+2)
 #pragma unroll
   for (int k = 0; k < 8; k++) {
     hmax[k] = max(hmax[k], dbl_hi(c[k]) & 0x7fffffff);
-    if (tab != nullptr && half == 0) tab[k * PBS] = c[k];
+    un[k] = c[k];
     const double lk = c[k] * rinv[k];
 #pragma unroll
     for (int jj = k + 1; jj < 8; jj++) c[jj] -= lk * Wm[jj * 8 + k];
     c[k] = lk;
+  }
+  // (stores after the chain: a store inside it would pin the multiplier loads of the later steps
+  // behind it, and this warp is the one everybody waits for)
+  if (tab != nullptr && half == 0) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) tab[k * PBS] = un[k];
   }
   if (half == 0) {
 #pragma unroll
