@@ -507,6 +507,7 @@ static __device__ __forceinline__ void block_row(int m, int j0, int nb, Work& W,
   double c0 = (valid && 2 * cg < nb) ? L[ca + rs] : 0.0;
   double c1 = (valid && 2 * cg + 1 < nb) ? L[cb + rs] : 0.0;
   int hmine = 0;
+  double own0 = 0.0, own1 = 0.0;                      // unscaled entries of this lane's two columns
 #pragma unroll
   for (int k = 0; k < 8; k++) {
     const double ck = __shfl_sync(FULL, (k & 1) ? c1 : c0, r + 8 * (k >> 1));
@@ -515,11 +516,15 @@ static __device__ __forceinline__ void block_row(int m, int j0, int nb, Work& W,
     const double lk = ck * rinv[k];
     if (2 * cg > k) c0 = fma(-lk, Wm[(2 * cg) * 8 + k], c0);
     if (2 * cg + 1 > k) c1 = fma(-lk, Wm[(2 * cg + 1) * 8 + k], c1);
-    if (cg == (k >> 1)) {
-      Wp[k * PBS + r] = ck;
-      if (k & 1) c1 = lk; else c0 = lk;
+    if (cg == (k >> 1)) {                           // the lanes that own column k
+      if (k & 1) { own1 = ck; c1 = lk; }
+      else { own0 = ck; c0 = lk; }
     }
   }
+  // (the unscaled entries are stored after the chain: a store inside it pins the multiplier loads
+  // of the later steps behind it)
+  Wp[(2 * cg) * PBS + r] = own0;
+  Wp[(2 * cg + 1) * PBS + r] = own1;
   if (valid && 2 * cg < nb) L[ca + row] = c0;
   if (valid && 2 * cg + 1 < nb) L[cb + row] = c1;
   if (lane < 8) atomicMax(&th[lane], hmine);          // (the other warps add their rows concurrently)
