@@ -342,14 +342,19 @@ static __device__ __forceinline__ void factor_ldl_fast(int m, Work& W, double be
       }
     } else if (warp == 0) {
       // reduce the split-K partials of tile 0, apply, eliminate
+      // (both loads of L before the stores: with L in global memory two read-modify-writes in
+      // program order are two memory round trips on the critical chain)
       const int row = j0 + g;
-#pragma unroll
-      for (int h = 0; h < 2; h++) {
-        const int col = 2 * tg + h;
-        const int e = g * 8 + col;
-        const double sum = (part[e] + part[64 + e]) + (part[128 + e] + part[192 + e]);
-        if (col < nb && row < m && row >= j0 + col) L[coff(j0 + col, m) + row] -= sum;
-      }
+      const int e0 = g * 8 + 2 * tg, e1 = e0 + 1;
+      const double s0 = (part[e0] + part[64 + e0]) + (part[128 + e0] + part[192 + e0]);
+      const double s1 = (part[e1] + part[64 + e1]) + (part[128 + e1] + part[192 + e1]);
+      const bool w0 = 2 * tg < nb && row < m && row >= j0 + 2 * tg;
+      const bool w1 = 2 * tg + 1 < nb && row < m && row >= j0 + 2 * tg + 1;
+      double* q0 = L + coff(min(j0 + 2 * tg, m - 1), m) + min(row, m - 1);
+      double* q1 = L + coff(min(j0 + 2 * tg + 1, m - 1), m) + min(row, m - 1);
+      const double v0 = *q0, v1 = *q1;
+      if (w0) *q0 = v0 - s0;
+      if (w1) *q1 = v1 - s1;
       // ---- step B: 8x8 diagonal block on warp 0, one matrix entry per lane ----
       __syncwarp();
       long long tb = phase_begin(W);
