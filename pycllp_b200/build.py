@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpycllp_b200.so")
 SOURCES = ["ipm_kernels.cu", "cabi.cu"]
-HEADERS = ["ipm_device.cuh", "ipm_types.h", "ipm_host.h", os.path.join("..", "..", "include", "pycllp_b200.h")]
+INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -26,7 +26,10 @@ def _stale():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    # every source and header the library is built from (csrc/*.cu, *.cuh, *.h, include/*.h)
+    deps = [os.path.abspath(__file__)]
+    for d in (CSRC, INCLUDE):
+        deps += [os.path.join(d, f) for f in os.listdir(d) if f.endswith((".cu", ".cuh", ".h"))]
     return any(os.path.getmtime(d) > t for d in deps)
 
 

@@ -102,7 +102,8 @@ int finish_setup(pycllp_b200_engine* e, int max_problems) {
   const int m = e->A.m, n = e->A.n;
   const size_t limit = e->smem_optin - 64;     // static smem (16 B) + margin
   int Ls = 1, Vs = 1;
-  if (smem_doubles(e->A, 1, 1) * 8 > limit) { Ls = 0; }
+  e->A.big = 0;
+  if (smem_doubles(e->A, 1, 1) * 8 > limit) { Ls = 0; e->A.big = 1; }
   if (smem_doubles(e->A, Ls, 1) * 8 > limit) { Vs = 0; }
   if (smem_doubles(e->A, Ls, Vs) * 8 > limit)
     return fail(e, PYCLLP_B200_ERR_ARG, "problem too large for the shared-memory work area");

@@ -82,6 +82,16 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "d"(a), "d"(b));
 }
 
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+// 8-byte shared-memory load that keeps its place in the instruction stream
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+
 // Per-block working set (pointers into shared memory or the block's scratch slot).
 struct Work {
   double *x, *z, *t, *d, *w;            // n each
@@ -92,6 +102,7 @@ struct Work {
   double* g1;                           // ldd : gather buffers of A_times2 (alias the work area)
   double* g2;
   double* tiles;                        // 2*TB*LDT : staging of the macro-tile SYRK (large problems only)
+  double* fb;                           // FB_DOUBLES of shared memory: multiplier-table chunks of factor_ldl_big
   double* L;                            // m(m+1)/2 packed column-major
   double* M;                            // m*m full symmetric (global scratch)
   double* red;                          // 256: reductions [0,32) + panel scratch (ipm_factor.cuh)
@@ -343,14 +354,46 @@ static __device__ __forceinline__ void form_M_dense(const Matrix& A, Work& W) {
   }
 }
 
-static __device__ __forceinline__ void form_M_sparse(const Matrix& A, Work& W) {
+// Sparse A: the entries of the shared pattern of A A' (lower triangle) from their (k, A_ik A_jk)
+// lists, straight into the packed factor storage, which is cleared first (the factorisation of
+// the previous step left its fill there).  keepM: also into the full symmetric M for the
+// refinement residual (the reference's sparse path has none, ldl.cl:698-711).
+static __device__ __forceinline__ void form_M_sparse(const Matrix& A, Work& W, bool keepM) {
   const int m = A.m;
-  for (int e = threadIdx.x; e < A.nme; e += NT) {
-    double s = 0.0;
-    for (int t = A.me_ptr[e]; t < A.me_ptr[e + 1]; t++) s += A.mt_w[t] * W.d[A.mt_k[t]];
-    int i = A.me_i[e], j = A.me_j[e];
-    W.M[(size_t)i * m + j] = s;
-    W.M[(size_t)j * m + i] = s;
+  {
+    double2* L2 = reinterpret_cast<double2*>(W.L);
+    const size_t n2 = packed_doubles(m) / 2;
+    for (size_t e = threadIdx.x; e < n2; e += NT) L2[e] = make_double2(0.0, 0.0);
+  }
+  __syncthreads();
+  // four entries per thread and round, their dependent loads (list bounds -> k -> d_k) issued
+  // side by side: one entry at a time is three serialised L2 round trips per entry
+  for (int e0 = threadIdx.x; e0 < A.nme; e0 += 4 * NT) {
+    int t0[4], t1[4], i[4], j[4], k[4];
+    double w[4], s[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int e = min(e0 + q * NT, A.nme - 1);
+      t0[q] = A.me_ptr[e]; t1[q] = A.me_ptr[e + 1];
+      i[q] = A.me_i[e]; j[q] = A.me_j[e];
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) { k[q] = A.mt_k[t0[q]]; w[q] = A.mt_w[t0[q]]; }   // every entry has >= 1 term
+#pragma unroll
+    for (int q = 0; q < 4; q++) s[q] = w[q] * W.d[k[q]];
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+      for (int t = t0[q] + 1; t < t1[q]; t++) s[q] += A.mt_w[t] * W.d[A.mt_k[t]];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      if (e0 + q * NT < A.nme) {
+        W.L[cidx(i[q], j[q], m)] = s[q];
+        if (keepM) {
+          W.M[(size_t)i[q] * m + j[q]] = s[q];
+          W.M[(size_t)j[q] * m + i[q]] = s[q];
+        }
+      }
+    }
   }
 }
 
@@ -459,7 +502,8 @@ template <bool LS, bool VS>
 static __device__ __forceinline__ void solve_normal(const Matrix& A, Work& W, const Params& p) {
   const int m = A.m, tid = threadIdx.x;
   long long t0 = phase_begin(W);
-  if (A.sparse) form_M_sparse(A, W);
+  const bool refine = p.max_refine > 0;
+  if (A.sparse) form_M_sparse(A, W, refine);
   else if (VS)                              // operand staged by TMA, needs the shared work area
     W.ring_g = form_M_dense_tma_call(A.sy_A, A.sy_seg, A.dcols, A.sing_ptr, A.sing_col, A.sing_w, A.m, A.nd,
                                      A.ldd, A.sy_ldm, A.sy_npass, W.d, W.dg, W.P, W.red, W.L, W.M, W.prof,
@@ -468,11 +512,9 @@ static __device__ __forceinline__ void solve_normal(const Matrix& A, Work& W, co
   __syncthreads();
   phase_end(W, 1, t0);
   t0 = phase_begin(W);
-  double bmax = 0.0;
-  for (int i = tid; i < m; i += NT) bmax = fmax(bmax, fabs(W.M[(size_t)i * m + i]));
-  const double beta = sqrt(block_max(bmax, W.red));
-  // the factorisation works in place on the packed lower triangle (the dense SYRK wrote it)
-  if (A.sparse || !VS) {
+  // the factorisation works in place on the packed lower triangle (the TMA SYRK and the sparse
+  // formation wrote it; the macro-tile SYRK of the largest dense problems wrote M only)
+  if (!A.sparse && !VS) {
     // (four loads in flight per thread: written element by element, the copy is one memory round
     // trip per element, since the compiler may not move a load of M across a store to L)
     for (int e0 = tid; e0 < m * m; e0 += 4 * NT) {
@@ -492,15 +534,26 @@ static __device__ __forceinline__ void solve_normal(const Matrix& A, Work& W, co
   }
   for (int i = tid; i < m; i += NT) W.dy[i] = 0.0;
   __syncthreads();
+  double bmax = 0.0;
+  for (int i = tid; i < m; i += NT) bmax = fmax(bmax, fabs(W.L[cidx(i, i, m)]));
+  const double beta = sqrt(block_max(bmax, W.red));
   phase_end(W, 6, t0);
   bool redo = true;
   const bool ahead = LS && m <= 208;                  // (L in shared memory: m <= ~202 in practice)
   if (ahead) redo = factor_ldl_ahead(m, W, beta, p.ldl_delta, W.RHS, W.S);
+  else if (!LS && m > SB) {                           // factor in global memory: super-panel sweep
+    factor_ldl_big(m, W, beta, p.ldl_delta, W.RHS, W.S);
+    redo = false;
+  }
   if (redo) {
     if (ahead) {                 // speculation failed somewhere: restore M and take the exact-capable path
-      for (int e = tid; e < m * m; e += NT) {
-        const int j = e / m, i = e - j * m;
-        if (i >= j) W.L[cidx(i, j, m)] = W.M[(size_t)j * m + i];
+      if (A.sparse && !refine) {
+        form_M_sparse(A, W, false);
+      } else {
+        for (int e = tid; e < m * m; e += NT) {
+          const int j = e / m, i = e - j * m;
+          if (i >= j) W.L[cidx(i, j, m)] = W.M[(size_t)j * m + i];
+        }
       }
       __syncthreads();
     }
@@ -510,6 +563,7 @@ static __device__ __forceinline__ void solve_normal(const Matrix& A, Work& W, co
   t0 = phase_begin(W);
   back_solve_fast(m, W);
   phase_end(W, 3, t0);
+  if (!refine) return;                                // (nobody would look at the residual)
   t0 = phase_begin(W);
   double maxr = residual_M(m, W);
   phase_end(W, 4, t0);

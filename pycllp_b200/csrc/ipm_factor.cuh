@@ -190,20 +190,20 @@ static __device__ __forceinline__ void diag_block(int m, int j0, int nb, Work& W
 // before the DMMAs of the current one.
 template <bool TWO>
 __device__ __forceinline__ void panel_update_tiles(const double* __restrict__ L,
-                                                   const double* __restrict__ P, int m, int j0,
+                                                   const double* __restrict__ P, int m, int kbase, int j0,
                                                    int tg, int g, int ra, int drow, double& c0,
                                                    double& c1, double& u0, double& u1) {
   double e0 = 0.0, e1 = 0.0, v0 = 0.0, v1 = 0.0;
   c0 = c1 = u0 = u1 = 0.0;
-  if (j0 == 0) return;
-  const double* pa = L + coff(tg, m) + ra;      // column k = tg, row ra
-  int d = 4 * m - 8 - 4 * tg;                   // coff(k + 4) - coff(k); decreases by 16 per step
+  if (j0 == kbase) return;
+  const double* pa = L + coff(kbase + tg, m) + ra;      // column k = kbase + tg, row ra
+  int d = 4 * m - 8 - 4 * (kbase + tg);         // coff(k + 4) - coff(k); decreases by 16 per step
   const double* pb = P + tg * NB + g;
   double a1, a2, a3 = 0.0, a4 = 0.0, b1, b2;
   a1 = pa[0]; if (TWO) a3 = pa[drow]; pa += d; d -= 16;
   a2 = pa[0]; if (TWO) a4 = pa[drow]; pa += d; d -= 16;
   b1 = pb[0]; b2 = pb[4 * NB]; pb += 8 * NB;
-  for (int k0 = 8; k0 < j0; k0 += 8) {
+  for (int k0 = kbase + 8; k0 < j0; k0 += 8) {
     double n1, n2, n3 = 0.0, n4 = 0.0;
     n1 = pa[0]; if (TWO) n3 = pa[drow]; pa += d; d -= 16;
     n2 = pa[0]; if (TWO) n4 = pa[drow]; pa += d; d -= 16;
@@ -222,9 +222,12 @@ __device__ __forceinline__ void panel_update_tiles(const double* __restrict__ L,
 }
 
 // Pre-condition: the lower triangle of M is stored in W.L (packed column-major).
-// rhs != nullptr: also computes Sf = (L D)^-1 rhs.
-static __device__ __forceinline__ void factor_ldl_fast(int m, Work& W, double beta, double delta,
-                                       const double* __restrict__ rhs, double* __restrict__ Sf) {
+// rhs != nullptr: also computes Sf = (L D)^-1 rhs  (rhs == Sf, in place, is allowed).
+// Panels [jbeg, jend) (jbeg a multiple of 8); the columns k < kbase have ALREADY been applied
+// to them (by super_update below), the loop applies the columns kbase <= k < j0.
+static __device__ __forceinline__ void factor_panels(int m, Work& W, double beta, double delta,
+                                                     const double* rhs, double* Sf, int jbeg, int jend,
+                                                     int kbase) {
   const int tid = threadIdx.x, lane = tid & 31, warp = warp_id();
   const int g = lane >> 2, tg = lane & 3;
   double* __restrict__ L = W.L;
@@ -240,9 +243,10 @@ static __device__ __forceinline__ void factor_ldl_fast(int m, Work& W, double be
   const double inv_beta2 = 1.0 / (beta * beta);
   int parity = 0;
 
-  for (int j0 = 0; j0 < m; j0 += NB, parity ^= 1) {
+  for (int j0 = jbeg; j0 < jend; j0 += NB, parity ^= 1) {
     const int nb = min(NB, m - j0);
     const int R = m - j0;
+    const int kw = j0 - kbase;                                // columns still to apply
     const int ntile = (R + 7) >> 3;
     int* th = thbuf + parity * 8;
     long long tq = phase_begin(W);
@@ -250,18 +254,18 @@ static __device__ __forceinline__ void factor_ldl_fast(int m, Work& W, double be
     // (four entries per thread and round: the loads are issued together -- the compiler cannot move a
     // load of L across a store to P on its own, and with L in global memory every round would be
     // one exposed L2 round trip)
-    for (int e0 = tid; e0 < j0 * NB; e0 += 4 * NT) {
+    for (int e0 = tid; e0 < kw * NB; e0 += 4 * NT) {
       double v[4];
 #pragma unroll
       for (int q = 0; q < 4; q++) {
         const int e = e0 + q * NT;
-        const int k = min(e, j0 * NB - 1) >> 3, jj = e & 7;
+        const int k = kbase + (min(e, kw * NB - 1) >> 3), jj = e & 7;
         v[q] = (jj < nb) ? L[coff(k, m) + j0 + jj] * D[k] : 0.0;
       }
 #pragma unroll
       for (int q = 0; q < 4; q++) {
         const int e = e0 + q * NT;
-        if (e < j0 * NB) P[e] = v[q];
+        if (e < kw * NB) P[e] = v[q];
       }
     }
     if (tid < 8) th[tid] = 0;
@@ -279,7 +283,7 @@ static __device__ __forceinline__ void factor_ldl_fast(int m, Work& W, double be
     //   A2. warp 0 (alone on sub-partition 0) reduces the partials and eliminates the block
     //       (step B) while the twelve warps of sub-partitions 1-3 update all other row tiles.
     double* part = P + (size_t)2 * m * NB;                   // [8][64] split-K partials
-    const int nks = j0 >> 2;                                  // k-steps of 4 columns
+    const int nks = kw >> 2;                                  // k-steps of 4 columns
     if (warp < 8 && (warp < 4 || with_rhs)) {
       const long long t0w = phase_begin(W);
       const int qw = warp & 3;
@@ -289,12 +293,12 @@ static __device__ __forceinline__ void factor_ldl_fast(int m, Work& W, double be
       const int rs = (row < m) ? row : j0;
       double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
       for (int ks = qw; ks < nks; ks += 8) {
-        const int ka = 4 * ks + tg, kb = ka + 16;
+        const int ka = kbase + 4 * ks + tg, kb = ka + 16;
         const bool hasb = ks + 4 < nks;
         double a1 = is_rhs ? Sf[ka] : L[coff(ka, m) + rs];
         double a2 = hasb ? (is_rhs ? Sf[kb] : L[coff(kb, m) + rs]) : 0.0;
-        const double b1 = P[ka * NB + g];
-        const double b2 = hasb ? P[kb * NB + g] : 0.0;
+        const double b1 = P[(ka - kbase) * NB + g];
+        const double b2 = hasb ? P[(kb - kbase) * NB + g] : 0.0;
         if (!ok) { a1 = 0.0; a2 = 0.0; }
         dmma884(c0, c1, a1, b1);
         if (hasb) dmma884(e0, e1, a2, b2);
@@ -317,8 +321,8 @@ static __device__ __forceinline__ void factor_ldl_fast(int m, Work& W, double be
         // row of the result, which is then simply not stored -- no masking in the loop
         const int ra = oka ? rowa : j0, rb = okb ? rowb : j0;
         double c0, c1, u0, u1;
-        if (two) panel_update_tiles<true>(L, P, m, j0, tg, g, ra, rb - ra, c0, c1, u0, u1);
-        else panel_update_tiles<false>(L, P, m, j0, tg, g, ra, 0, c0, c1, u0, u1);
+        if (two) panel_update_tiles<true>(L, P, m, kbase, j0, tg, g, ra, rb - ra, c0, c1, u0, u1);
+        else panel_update_tiles<false>(L, P, m, kbase, j0, tg, g, ra, 0, c0, c1, u0, u1);
         // L -= acc: all four loads first, then the stores (written as four read-modify-writes the
         // compiler keeps them in order, and with L in global memory that is four L2 round trips
         // per tile pair -- 7 % of all warp samples at config 5)
@@ -454,6 +458,274 @@ static __device__ __forceinline__ void factor_ldl_fast(int m, Work& W, double be
       __syncthreads();
     }
     phase_end(W, 11, tq);
+  }
+}
+
+static __device__ __forceinline__ void factor_ldl_fast(int m, Work& W, double beta, double delta,
+                                                       const double* rhs, double* Sf) {
+  factor_panels(m, W, beta, delta, rhs, Sf, 0, m, 0);
+}
+
+// ---------------------------------------------------------------------------------------
+// factor_ldl_big: the same factorisation for factors that live in GLOBAL memory (m > ~208:
+// config 5, m = 500, L = 1 MB; config 4, m = 2000, L = 16 MB).  Left-looking by SUPER-PANELS
+// of SB = 64 columns: one GEMM  L(J0.., J0..J0+63) -= L(J0.., 0..J0-1) T,  T[k][c] =
+// D_k L(J0+c, k),  brings in every earlier column at once, then the eight 8-column panels of
+// the super-panel are factorised by factor_panels with kbase = J0 (columns inside the
+// super-panel only).  L(:, k < J0) is thus streamed m/64 times per factorisation instead of
+// m/8 times (config 4: 166 MB instead of 1.3 GB per LP and Newton step).
+//
+// super_update, the GEMM (FP64 tensor cores, DMMA m8n8k4):
+//   * a warp owns a unit of 16 rows x 64 columns: 16 accumulator tiles = 64 registers; the A
+//     fragment of its two interleaved 8-row tiles (even / odd rows) is ONE 16-byte word per lane
+//     and k-step (4 columns x 16 consecutive rows = four 128-byte runs per warp), copied by
+//     cp.async into a per-lane ring of 8 slots seven k-steps ahead of its use (28 KB in flight per
+//     SM: enough for HBM latency at config 4);
+//   * the multiplier table T is built cooperatively in chunks of 32 k-rows, double buffered in
+//     shared memory (row stride 68 = 4 mod 16: conflict-free B fragments), one __syncthreads per
+//     chunk; the global loads of the next chunk are issued before the DMMAs of the current one;
+//   * the rows of a super-panel are processed in passes of 16 units (256 rows); what is left over
+//     (and the diagonal block) goes as 16x16 items, four warps per row unit, so that partial
+//     passes still use all warps; the right-hand-side row (Sf, kept in place) is accumulated by
+//     the threads that build T, four FMAs per chunk each.
+// Per k-step a warp issues 16 DMMAs for 512 bytes of L: 8 B/cycle per SM at the DMMA rate,
+// well under the 20-35 B/cycle an SM gets from L2.
+// ---------------------------------------------------------------------------------------
+constexpr int SB = 64;                               // super-panel width
+constexpr int SB_KCH = 32;                           // k-rows of T per shared-memory chunk
+constexpr int SB_LDT = SB + 4;                       // row stride of T
+constexpr int SB_NST = SB_KCH / 4;                   // A-operand ring: one stage per k-step of a chunk
+constexpr int SB_RING = SB_NST * 32 * 2;             // doubles per warp (16 bytes per lane and stage)
+constexpr int FB_T = 2 * SB_KCH * SB_LDT;            // the two T buffers (34 KB)
+static_assert(FB_T + NWARP * SB_RING == FB_DOUBLES, "FB_DOUBLES (ipm_types.h) out of date");
+
+__device__ __forceinline__ void cp_async16_cg(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16_ca(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ double2 lds_f64x2(uint32_t addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  return v;
+}
+
+// Everything of super_update that is the same for all passes.
+struct SuCtx {
+  int m, J0, nbw, nch;
+  double* L;
+  const double* D;
+  const double* Sf;
+  double* T;
+  uint32_t ring;       // shared-memory address of this lane's first ring slot
+  int kk, c4;          // T build: this thread's k-row inside a chunk and its four columns
+  double r[4];         // right-hand-side row: partial sums of Sf[k] T[k][c4..c4+3]
+  int buf;             // T buffer in use
+};
+
+// chunk `ch` of T: the raw global loads (issued a whole chunk of DMMAs before their use) ...
+struct SuT { double2 t0, t1; double dk, sk; };
+__device__ __forceinline__ void su_t_load(const SuCtx& c, int ch, bool rhs, SuT& t) {
+  const int k = ch * SB_KCH + c.kk;
+  t.dk = c.D[k];
+  t.sk = rhs ? c.Sf[k] : 0.0;
+  const double* src = c.L + coff(k, c.m) + c.J0;
+  if (c.nbw == SB) {
+    t.t0 = *reinterpret_cast<const double2*>(src + c.c4);
+    t.t1 = *reinterpret_cast<const double2*>(src + c.c4 + 2);
+  } else {                                           // last super-panel: rows J0+c >= m do not exist
+    const int nb1 = c.nbw - 1, c4 = c.c4;
+    t.t0.x = src[min(c4, nb1)];     t.t0.y = src[min(c4 + 1, nb1)];
+    t.t1.x = src[min(c4 + 2, nb1)]; t.t1.y = src[min(c4 + 3, nb1)];
+  }
+}
+// ... and their use: T[k][c] = D_k L(J0+c, k) into buffer `buf`; the right-hand-side row
+// accumulates Sf[k] T[k][c] (sk = 0 when it is not this pass' job)
+__device__ __forceinline__ void su_t_store(SuCtx& c, int buf, SuT& t) {
+  if (c.nbw != SB) {
+    const int c4 = c.c4;
+    if (c4 >= c.nbw) t.t0.x = 0.0;
+    if (c4 + 1 >= c.nbw) t.t0.y = 0.0;
+    if (c4 + 2 >= c.nbw) t.t1.x = 0.0;
+    if (c4 + 3 >= c.nbw) t.t1.y = 0.0;
+  }
+  t.t0.x *= t.dk; t.t0.y *= t.dk; t.t1.x *= t.dk; t.t1.y *= t.dk;
+  c.r[0] = fma(t.sk, t.t0.x, c.r[0]); c.r[1] = fma(t.sk, t.t0.y, c.r[1]);
+  c.r[2] = fma(t.sk, t.t1.x, c.r[2]); c.r[3] = fma(t.sk, t.t1.y, c.r[3]);
+  double* dst = c.T + buf * (SB_KCH * SB_LDT) + c.kk * SB_LDT + c.c4;
+  *reinterpret_cast<double2*>(dst) = t.t0;
+  *reinterpret_cast<double2*>(dst + 2) = t.t1;
+}
+
+// One pass: this warp accumulates a 16-row x (8 NCT)-column item over all k < J0 and subtracts
+// it from the panel.  rows ra .. ra+15, columns J0 + col0 ...  first: the right-hand-side row
+// is accumulated by the T-build threads during this pass; more: another pass follows (its
+// first T chunk is prefetched during this pass' last one).
+template <int NCT>
+__device__ __forceinline__ void su_pass(SuCtx& c, bool active, int ra, int col0, bool first, bool more) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
+  const int m = c.m, J0 = c.J0;
+  double cx[NCT][2], cy[NCT][2];                     // even-row / odd-row tiles x NCT column tiles
+#pragma unroll
+  for (int t = 0; t < NCT; t++) cx[t][0] = cx[t][1] = cy[t][0] = cy[t][1] = 0.0;
+  // A operand: rows ra+2g, ra+2g+1 of column k0+tg = one 16-byte word per lane and k-step, copied
+  // global -> this lane's ring slot by cp.async (no registers held while in flight) SB_NST-1
+  // k-steps ahead; every lane reads back exactly the word it copied, so no barrier is needed
+  const double* pa = c.L + coff(tg, m) + ra + 2 * g;
+  int d = 4 * m - 8 - 4 * tg;                        // coff(k + 4) - coff(k); decreases by 16 per k-step
+  int ksleft = active ? J0 / 4 : 0;                  // k-steps of this pass not yet issued
+  auto a_issue = [&](int stage) {
+    if (ksleft > 0) {
+      if (NCT == 8) cp_async16_cg(c.ring + stage * 512, pa);
+      else cp_async16_ca(c.ring + stage * 512, pa);  // four warps share these rows: keep them in L1
+      pa += d; d -= 16; ksleft--;
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int s = 0; s < SB_NST - 1; s++) a_issue(s);
+#pragma unroll 1
+  for (int ch = 0; ch < c.nch; ch++) {
+    SuT tn;
+    tn.t0 = tn.t1 = make_double2(0.0, 0.0); tn.dk = tn.sk = 0.0;
+    const bool last = ch + 1 == c.nch;
+    const bool nxt = !last || more;
+    if (nxt) su_t_load(c, last ? 0 : ch + 1, first && !last, tn);
+    if (active) {
+      const uint32_t tb = smem_u32(c.T + c.buf * (SB_KCH * SB_LDT) + tg * SB_LDT + col0 + g);
+#pragma unroll
+      for (int ks = 0; ks < SB_NST; ks++) {
+        a_issue((ks + SB_NST - 1) % SB_NST);
+        cp_async_wait<SB_NST - 1>();
+        const double2 a = lds_f64x2(c.ring + ks * 512);
+#pragma unroll
+        for (int h = 0; h < NCT; h += 4) {
+          double b[4];
+#pragma unroll
+          for (int t = 0; t < 4 && h + t < NCT; t++) b[t] = lds_f64(tb + 8 * (ks * 4 * SB_LDT + 8 * (h + t)));
+#pragma unroll
+          for (int t = 0; t < 4 && h + t < NCT; t++) {
+            dmma884(cx[h + t][0], cx[h + t][1], a.x, b[t]);
+            dmma884(cy[h + t][0], cy[h + t][1], a.y, b[t]);
+          }
+        }
+      }
+    }
+    if (nxt) su_t_store(c, c.buf ^ 1, tn);
+    __syncthreads();
+    c.buf ^= 1;
+  }
+  cp_async_wait<0>();
+  if (!active) return;
+  // epilogue: panel -= accumulators
+  if (c.nbw == SB && ra >= J0 + SB && ra + 16 <= m) {
+    // interior item: rows ra+2g, ra+2g+1 of a column are one aligned 16-byte word
+    // (four loads, then four stores: read-modify-writes in program order would be
+    // serialised L2 round trips)
+    double* base = c.L + ra + 2 * g;
+#pragma unroll
+    for (int t = 0; t < NCT; t += 2) {
+      double2* q[4];
+      double2 v[4];
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        const int col = J0 + col0 + 8 * (t + (e >> 1)) + 2 * tg + (e & 1);
+        q[e] = reinterpret_cast<double2*>(base + coff(col, m));
+        v[e] = *q[e];
+      }
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        v[e].x -= cx[t + (e >> 1)][e & 1];
+        v[e].y -= cy[t + (e >> 1)][e & 1];
+        *q[e] = v[e];
+      }
+    }
+  } else {
+    // item on the diagonal block / at the ragged end: element-wise, only i >= col, i < m
+#pragma unroll
+    for (int t = 0; t < NCT; t++) {
+      double* q[4];
+      double v[4];
+      bool ok[4];
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        const int cc = col0 + 8 * t + 2 * tg + (e & 1);
+        const int row = ra + 2 * g + (e >> 1);
+        ok[e] = cc < c.nbw && row < m && row >= J0 + cc;
+        q[e] = c.L + coff(min(J0 + cc, m - 1), m) + (ok[e] ? row : m - 1);
+        v[e] = *q[e];
+      }
+      if (ok[0]) *q[0] = v[0] - cx[t][0];
+      if (ok[1]) *q[1] = v[1] - cx[t][1];
+      if (ok[2]) *q[2] = v[2] - cy[t][0];
+      if (ok[3]) *q[3] = v[3] - cy[t][1];
+    }
+  }
+}
+
+// fb: FB_DOUBLES of shared memory (T buffers, then the warps' A rings)
+static __device__ __noinline__ void super_update(int m, int J0, int nbw, double* L, const double* D,
+                                                 double* Sf, double* fb) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = warp_id();
+  SuCtx c;
+  c.m = m; c.J0 = J0; c.nbw = nbw; c.nch = J0 / SB_KCH;   // (J0 is a multiple of SB)
+  c.L = L; c.D = D; c.Sf = Sf; c.T = fb;
+  c.ring = smem_u32(fb + FB_T + warp * SB_RING) + lane * 16;
+  c.kk = tid >> 4; c.c4 = (tid & 15) * 4;
+  c.r[0] = c.r[1] = c.r[2] = c.r[3] = 0.0;
+  c.buf = 0;
+  {
+    SuT t;
+    su_t_load(c, 0, true, t);
+    su_t_store(c, 0, t);
+  }
+  __syncthreads();
+  // rows J0 .. m-1 in units of 16: the `rem` topmost units (they include the diagonal block) are
+  // cut into four 16x16 items each so that a partial pass still occupies all sixteen warps (and
+  // the items above the diagonal are skipped); the rest goes in full passes of 16x64 units
+  const int nunit = (m - J0 + 15) >> 4;
+  const int nfull = nunit >> 4, rem = nunit & 15;
+  const int nq = (rem + 3) >> 2;
+  for (int pss = 0; pss < nfull; pss++) {
+    const int ru = rem + pss * NWARP + warp;
+    su_pass<8>(c, true, J0 + 16 * ru, 0, pss == 0, pss + 1 < nfull || nq > 0);
+  }
+  for (int q = 0; q < nq; q++) {
+    const int ru = q * 4 + (warp >> 2), cg = warp & 3;
+    const bool active = ru < rem && ru >= cg && 16 * cg < nbw;
+    su_pass<2>(c, active, J0 + 16 * ru, 16 * cg, nfull == 0 && q == 0, q + 1 < nq);
+  }
+  // right-hand-side row: reduce the partial sums of the 32 k-rows
+  double* part = fb;
+#pragma unroll
+  for (int e = 0; e < 4; e++) part[tid * 4 + e] = c.r[e];
+  __syncthreads();
+  if (tid < nbw) {
+    double sum = 0.0;
+#pragma unroll 8
+    for (int k = 0; k < SB_KCH; k++) sum += part[(k * 16 + (tid >> 2)) * 4 + (tid & 3)];
+    Sf[J0 + tid] -= sum;
+  }
+  __syncthreads();
+}
+
+// Sf <- (L D)^-1 rhs rides along (in place).  Requires W.fb: FB_DOUBLES of shared memory.
+static __device__ __forceinline__ void factor_ldl_big(int m, Work& W, double beta, double delta,
+                                                      const double* __restrict__ rhs, double* Sf) {
+  for (int i = threadIdx.x; i < m; i += NT) Sf[i] = rhs[i];
+  __syncthreads();
+  for (int J0 = 0; J0 < m; J0 += SB) {
+    const int nbw = min(SB, m - J0);
+    if (J0 > 0) {
+      const long long t0 = phase_begin(W);
+      super_update(m, J0, nbw, W.L, W.D, Sf, W.fb);
+      phase_end(W, 14, t0);
+    }
+    factor_panels(m, W, beta, delta, Sf, Sf, J0, J0 + nbw, J0);
   }
 }
 

@@ -21,10 +21,12 @@ static __device__ __forceinline__ void carve(const Matrix& A, const Scratch& sc,
   if constexpr (VS) {
     W.P = smem + o; o += align16(psz);
     W.tiles = nullptr;
+    W.fb = W.P;                 // (work_area() >= FB_DOUBLES whenever the big factor can run)
     v = smem + o; o += align16((size_t)4 * n + nw + 6 * m);
     W.dg = v + 4 * (size_t)n;   // = W.w (max(n, ldd) doubles): dead between prepare_rhs and step
   } else {   // large problems: only the reduction scratch and the SYRK macro tiles stay on-chip
     W.tiles = smem + o; o += 2 * TB * LDT;
+    W.fb = smem + o; o += FB_DOUBLES;
     W.P = slot + sc.off_P;
     W.dg = slot + sc.off_dg;
     v = slot + sc.off_vec;
@@ -119,7 +121,7 @@ ipm_solve_kernel(Matrix A, Batch B, Scratch sc, Params p) {
   carve<LS, VS>(A, sc, smem, W);
   if (W.prof && threadIdx.x < 16) reinterpret_cast<unsigned long long*>(W.red + RED_PROF)[threadIdx.x] = 0;
   ring_init(W);
-  if (A.sparse) {   // entries outside the pattern of A A' are never written again
+  if (A.sparse && p.max_refine > 0) {   // entries outside the pattern of A A' are never written again
     const size_t mm = (size_t)A.m * A.m;
     for (size_t e = threadIdx.x; e < mm; e += NT) W.M[e] = 0.0;
     __syncthreads();
@@ -181,7 +183,7 @@ size_t smem_doubles(const Matrix& A, int L_in_smem, int vec_in_smem) {
   if (vec_in_smem) {
     o += al(work_area_doubles(A)) + al(vec_area_doubles(A));
   } else {
-    o += 2 * TB * LDT;
+    o += 2 * TB * LDT + FB_DOUBLES;
   }
   const size_t g = (size_t)2 * (A.ldd > 0 ? A.ldd : 1);
   if (L_in_smem) o += packed_doubles(A.m) > g ? packed_doubles(A.m) : g;

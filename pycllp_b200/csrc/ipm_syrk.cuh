@@ -19,9 +19,6 @@ namespace pb200 {
 
 constexpr int RED_MBAR = 216;   // SY_STAGES 8-byte mbarriers + SY_STAGES int counters inside W.red (216..223)
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
@@ -53,12 +50,6 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
       : "memory");
 }
 
-// 8-byte shared-memory load that keeps its place in the instruction stream
-__device__ __forceinline__ double lds_f64(uint32_t addr) {
-  double v;
-  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
-  return v;
-}
 // The TMA ring (SY_STAGES stages in W.P, one mbarrier + one counter each) is initialised ONCE
 // per kernel: re-initialising a live mbarrier object is undefined behaviour (seen: a hang at
 // one call site).  Every user continues the global chunk count W.ring_g, which fixes stage

@@ -15,6 +15,7 @@ constexpr int SY_KC = 8;         // TMA-staged SYRK: packed columns per chunk
 constexpr int SY_STAGES = 3;     //   chunks in flight (ring of shared-memory stages)
 constexpr int SY_SEG = 3;        //   segments per warp per pass
 constexpr int SY_CW = 4;         //   8x8 tiles per segment
+constexpr int FB_DOUBLES = 2 * 32 * 68 + 16 * 8 * 64;   // shared memory of factor_ldl_big: two T chunks + 16 A rings
 
 struct Params {
   double eps, delta, r, ldl_delta, refine_tol;
@@ -24,6 +25,7 @@ struct Params {
 // The shared constraint matrix and everything precomputed from it at setup.
 struct Matrix {
   int m, n, sparse;
+  int big;                 // the factor lives in global memory (factor_ldl_big needs FB_DOUBLES of work area)
   // dense operator (row-major m x n)
   const double* A;
   // SYRK operand: the nd columns of A with >= 2 non-zeros, packed m x ldd row-major
@@ -69,6 +71,7 @@ inline size_t work_area(const Matrix& A) {
   if (psz < st) psz = st;
   if (psz < g) psz = g;
   if (psz < tb) psz = tb;
+  if (A.big && psz < (size_t)FB_DOUBLES) psz = FB_DOUBLES;   // factor_ldl_big (ipm_factor.cuh)
   return psz;
 }
 // doubles of the vector W.w, which also serves as the gather of d on the packed SYRK columns
