@@ -541,12 +541,10 @@ static __device__ __forceinline__ void solve_normal(const Matrix& A, Work& W, co
   bool redo = true;
   const bool ahead = LS && m <= 208;                  // (L in shared memory: m <= ~202 in practice)
   if (ahead) redo = factor_ldl_ahead(m, W, beta, p.ldl_delta, W.RHS, W.S);
-  else if (!LS && m > SB) {                           // factor in global memory: super-panel sweep
-    factor_ldl_big(m, W, beta, p.ldl_delta, W.RHS, W.S);
-    redo = false;
-  }
+  const bool big = !LS && m > SB;                     // factor in global memory: super-panel sweep
+  if (big) redo = factor_ldl_big(m, W, beta, p.ldl_delta, W.RHS, W.S);
   if (redo) {
-    if (ahead) {                 // speculation failed somewhere: restore M and take the exact-capable path
+    if (ahead || big) {          // speculation failed somewhere: restore M and take the exact-capable path
       if (A.sparse && !refine) {
         form_M_sparse(A, W, false);
       } else {

@@ -225,9 +225,10 @@ __device__ __forceinline__ void panel_update_tiles(const double* __restrict__ L,
 // rhs != nullptr: also computes Sf = (L D)^-1 rhs  (rhs == Sf, in place, is allowed).
 // Panels [jbeg, jend) (jbeg a multiple of 8); the columns k < kbase have ALREADY been applied
 // to them (by super_update below), the loop applies the columns kbase <= k < j0.
-static __device__ __forceinline__ void factor_panels(int m, Work& W, double beta, double delta,
+static __device__ __forceinline__ bool factor_panels(int m, Work& W, double beta, double delta,
                                                      const double* rhs, double* Sf, int jbeg, int jend,
                                                      int kbase) {
+  bool any_exact = false;
   const int tid = threadIdx.x, lane = tid & 31, warp = warp_id();
   const int g = lane >> 2, tg = lane & 3;
   double* __restrict__ L = W.L;
@@ -440,6 +441,7 @@ static __device__ __forceinline__ void factor_panels(int m, Work& W, double beta
       bad = __any_sync(0xffffffffu, mine);
     }
     if (bad) {
+      any_exact = true;
       // restore the updated-but-uneliminated panel and redo it by the sequential rule
       if (tid == 0) {
         for (int i = 0; i < nb; i++)
@@ -459,6 +461,7 @@ static __device__ __forceinline__ void factor_panels(int m, Work& W, double beta
     }
     phase_end(W, 11, tq);
   }
+  return any_exact;
 }
 
 static __device__ __forceinline__ void factor_ldl_fast(int m, Work& W, double beta, double delta,
@@ -497,7 +500,7 @@ constexpr int SB_LDT = SB + 4;                       // row stride of T
 constexpr int SB_NST = SB_KCH / 4;                   // A-operand ring: one stage per k-step of a chunk
 constexpr int SB_RING = SB_NST * 32 * 2;             // doubles per warp (16 bytes per lane and stage)
 constexpr int FB_T = 2 * SB_KCH * SB_LDT;            // the two T buffers (34 KB)
-static_assert(FB_T + NWARP * SB_RING == FB_DOUBLES, "FB_DOUBLES (ipm_types.h) out of date");
+static_assert(FB_T + NWARP * SB_RING + SB * SB_LDT + SB + SB / 2 == FB_DOUBLES, "FB_DOUBLES (ipm_types.h) out of date");
 
 __device__ __forceinline__ void cp_async16_cg(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -514,6 +517,19 @@ __device__ __forceinline__ double2 lds_f64x2(uint32_t addr) {
   return v;
 }
 
+struct SuT { double2 t0, t1; double dk, sk; };   // one thread's share of a T chunk, in flight
+
+// four 16-byte shared-memory loads 64 bytes apart as ONE statement: left to itself ptxas funnels
+// them through one register quad (load, use, load, use ...) and every use waits a full
+// shared-memory round trip
+__device__ __forceinline__ void lds_f64x2_x4(uint32_t addr, double2 (&w)[4]) {
+  asm volatile("ld.shared.v2.f64 {%0,%1}, [%8];\n\tld.shared.v2.f64 {%2,%3}, [%8+64];\n\t"
+               "ld.shared.v2.f64 {%4,%5}, [%8+128];\n\tld.shared.v2.f64 {%6,%7}, [%8+192];"
+               : "=d"(w[0].x), "=d"(w[0].y), "=d"(w[1].x), "=d"(w[1].y), "=d"(w[2].x), "=d"(w[2].y),
+                 "=d"(w[3].x), "=d"(w[3].y)
+               : "r"(addr));
+}
+
 // Everything of super_update that is the same for all passes.
 struct SuCtx {
   int m, J0, nbw, nch;
@@ -522,13 +538,22 @@ struct SuCtx {
   const double* Sf;
   double* T;
   uint32_t ring;       // shared-memory address of this lane's first ring slot
+  double* blk;         // packed nbw x nbw diagonal block (shared memory)
+  double* Wm;          // [64][SB_LDT] k-major: Wm[k][j] = D_k L11[j][k], j > k
+  double* rinv;        // [64] 1/D_k
+  int* th;             // [64] hi-words of max |c_ik| over the rows below the block
+  const Work* W;       // (phase counters)
   int kk, c4;          // T build: this thread's k-row inside a chunk and its four columns
   double r[4];         // right-hand-side row: partial sums of Sf[k] T[k][c4..c4+3]
   int buf;             // T buffer in use
+  // T pipeline of the current group of K-loop passes: chunk g (of gtot, contents g mod nch) is
+  // in buffer `buf`; with look-ahead 2 (the short chunks of the 16x16 passes) chunk g+1 waits in tn
+  int g, gtot;
+  bool rhs;            // this group accumulates the right-hand-side row (during its first sweep)
+  SuT tn;
 };
 
 // chunk `ch` of T: the raw global loads (issued a whole chunk of DMMAs before their use) ...
-struct SuT { double2 t0, t1; double dk, sk; };
 __device__ __forceinline__ void su_t_load(const SuCtx& c, int ch, bool rhs, SuT& t) {
   const int k = ch * SB_KCH + c.kk;
   t.dk = c.D[k];
@@ -561,69 +586,263 @@ __device__ __forceinline__ void su_t_store(SuCtx& c, int buf, SuT& t) {
   *reinterpret_cast<double2*>(dst + 2) = t.t1;
 }
 
-// One pass: this warp accumulates a 16-row x (8 NCT)-column item over all k < J0 and subtracts
-// it from the panel.  rows ra .. ra+15, columns J0 + col0 ...  first: the right-hand-side row
-// is accumulated by the T-build threads during this pass; more: another pass follows (its
-// first T chunk is prefetched during this pass' last one).
+static __device__ __forceinline__ bool factor_ldl_ahead(int m, Work& W, double beta, double delta,
+                                                        const double* rhs, double* __restrict__ Sf);
+
+// Row solve of a 16-row x 64-column unit against the factorised 64x64 diagonal block, in
+// registers, in the accumulator layout of the DMMAs (cx: rows ra+2g, cy: rows ra+2g+1; tile t
+// holds columns 8t+2tg, 8t+2tg+1), and store of the finished columns.  Same arithmetic as step
+// C of factor_panels, column by column:  l_k = c_k / D_k ;  c_j -= l_k (D_k L11[j][k])  for
+// j > k  -- c_k is broadcast over the four lanes that share a row (one shuffle per row and
+// column), every lane then updates the columns it owns with plain FMAs (16 on average, all
+// independent).  No DMMAs here on purpose: FP64 FMAs queue behind the DMMAs of their SM
+// sub-partition and the warps of a sub-partition are at different columns.
+// The loop over the eight column tiles is NOT unrolled: the finished tile is stored and the
+// others move down one register set, so the body always works on tile 0 (fully unrolled, the
+// 64 columns are 46 KB of code and the warps miss in the instruction cache on every line).
+// WmT[k][j] = D_k L11[j][k] (k-major, row stride SB_LDT: the two columns a lane owns in a tile
+// are one 16-byte word), rinv[k] = 1/D_k.  hmA/hmB: hi-words of max |c_k| over the rows of this
+// warp for column lane / 32+lane (the theta check of the speculative factorisation); vx, vy:
+// row exists; dst: &L(r0, J0 + 2 tg) ; cstep[t]: not needed -- column offsets come from coff.
+__device__ __forceinline__ void trsm_unit(double (&cx)[8][2], double (&cy)[8][2],
+                                          const double* __restrict__ WmT,
+                                          const double* __restrict__ rinv, bool vx, bool vy,
+                                          int& hmA, int& hmB, double* __restrict__ L, int m, int J0,
+                                          int r0, bool interior) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31, tg = lane & 3;
+  const int grp = lane & ~3;
+#pragma unroll 1
+  for (int tk = 0; tk < 8; tk++) {
+    const int nt = 7 - tk;                           // tiles behind the current one
+    const uint32_t wb = smem_u32(WmT + (8 * tk) * SB_LDT + 8 * tk + 2 * tg);
+    const double* rv = rinv + 8 * tk;
+    int hm = 0;
+#pragma unroll
+    for (int kk = 0; kk < 8; kk++) {
+      const int src = grp | (kk >> 1);
+      const double ckx = __shfl_sync(FULL, cx[0][kk & 1], src);
+      const double cky = __shfl_sync(FULL, cy[0][kk & 1], src);
+      const int hx = vx ? (dbl_hi(ckx) & 0x7fffffff) : 0, hy = vy ? (dbl_hi(cky) & 0x7fffffff) : 0;
+      const int h = __reduce_max_sync(FULL, max(hx, hy));
+      if ((lane & 7) == kk) hm = h;
+      const double r = rv[kk];
+      const double lx = ckx * r, ly = cky * r;
+      // (the table words of four tiles are fetched together, ahead of the branches on nt: a load
+      // inside each branch is one exposed shared-memory round trip per tile and column; words
+      // past the last tile are garbage inside the work area and are not used)
+      double2 w[4];
+      lds_f64x2_x4(wb + 8 * (kk * SB_LDT), w);
+      if (2 * tg > kk) { cx[0][0] = fma(-lx, w[0].x, cx[0][0]); cy[0][0] = fma(-ly, w[0].x, cy[0][0]); }
+      if (2 * tg + 1 > kk) { cx[0][1] = fma(-lx, w[0].y, cx[0][1]); cy[0][1] = fma(-ly, w[0].y, cy[0][1]); }
+#pragma unroll
+      for (int j = 1; j < 4; j++) {
+        if (j <= nt) {
+          cx[j][0] = fma(-lx, w[j].x, cx[j][0]); cy[j][0] = fma(-ly, w[j].x, cy[j][0]);
+          cx[j][1] = fma(-lx, w[j].y, cx[j][1]); cy[j][1] = fma(-ly, w[j].y, cy[j][1]);
+        }
+      }
+      if (nt >= 4) {
+        lds_f64x2_x4(wb + 8 * (kk * SB_LDT + 32), w);
+#pragma unroll
+        for (int j = 4; j < 8; j++) {
+          if (j <= nt) {
+            cx[j][0] = fma(-lx, w[j - 4].x, cx[j][0]); cy[j][0] = fma(-ly, w[j - 4].x, cy[j][0]);
+            cx[j][1] = fma(-lx, w[j - 4].y, cx[j][1]); cy[j][1] = fma(-ly, w[j - 4].y, cy[j][1]);
+          }
+        }
+      }
+      if (tg == (kk >> 1)) { cx[0][kk & 1] = lx; cy[0][kk & 1] = ly; }
+    }
+    // column 8 tk + (lane & 7) of the theta maxima: lanes 8 (tk & 3) .. +7 of hmA (tk < 4) / hmB
+    if ((lane >> 3) == (tk & 3)) {
+      if (tk < 4) hmA = max(hmA, hm);
+      else hmB = max(hmB, hm);
+    }
+    // finished tile -> L, the others move down
+#pragma unroll
+    for (int hh = 0; hh < 2; hh++) {
+      double* q = L + coff(J0 + 8 * tk + 2 * tg + hh, m) + r0;
+      if (interior) *reinterpret_cast<double2*>(q) = make_double2(cx[0][hh], cy[0][hh]);
+      else {
+        if (vx) q[0] = cx[0][hh];
+        if (vy) q[1] = cy[0][hh];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 7; j++) {
+      cx[j][0] = cx[j + 1][0]; cx[j][1] = cx[j + 1][1];
+      cy[j][0] = cy[j + 1][0]; cy[j][1] = cy[j + 1][1];
+    }
+  }
+}
+
+// What a pass does with its accumulators.
+constexpr int SU_RMW = 0;    // 16x16 item below the diagonal block: panel -= acc (global)
+constexpr int SU_DIAG = 1;   // 16x16 item of the diagonal block: (panel - acc) -> shared-memory block
+constexpr int SU_TRSM = 2;   // 16x64 unit below the diagonal block: (panel - acc), row solve, -> global
+
+// One pass: this warp accumulates a 16-row x (8 NCT)-column item over all k < J0 (kloop) and
+// finishes it according to `mode`.  rows ra .. ra+15, columns J0 + col0 ...  first: the
+// right-hand-side row is accumulated by the T-build threads during this pass; more: another
+// K-loop pass follows (its first T chunk is prefetched during this pass' last one).
 template <int NCT>
-__device__ __forceinline__ void su_pass(SuCtx& c, bool active, int ra, int col0, bool first, bool more) {
+__device__ __forceinline__ void su_pass(SuCtx& c, int mode, bool active, int ra, int col0, bool kloop) {
+  constexpr int LA = (NCT == 2) ? 2 : 1;             // T look-ahead in chunks
   const int lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
   const int m = c.m, J0 = c.J0;
   double cx[NCT][2], cy[NCT][2];                     // even-row / odd-row tiles x NCT column tiles
 #pragma unroll
   for (int t = 0; t < NCT; t++) cx[t][0] = cx[t][1] = cy[t][0] = cy[t][1] = 0.0;
-  // A operand: rows ra+2g, ra+2g+1 of column k0+tg = one 16-byte word per lane and k-step, copied
-  // global -> this lane's ring slot by cp.async (no registers held while in flight) SB_NST-1
-  // k-steps ahead; every lane reads back exactly the word it copied, so no barrier is needed
-  const double* pa = c.L + coff(tg, m) + ra + 2 * g;
-  int d = 4 * m - 8 - 4 * tg;                        // coff(k + 4) - coff(k); decreases by 16 per k-step
-  int ksleft = active ? J0 / 4 : 0;                  // k-steps of this pass not yet issued
-  auto a_issue = [&](int stage) {
-    if (ksleft > 0) {
-      if (NCT == 8) cp_async16_cg(c.ring + stage * 512, pa);
-      else cp_async16_ca(c.ring + stage * 512, pa);  // four warps share these rows: keep them in L1
-      pa += d; d -= 16; ksleft--;
-    }
-    cp_async_commit();
-  };
+  if (kloop) {
+    // A operand: rows ra+2g, ra+2g+1 of column k0+tg = one 16-byte word per lane and k-step, copied
+    // global -> this lane's ring slot by cp.async (no registers held while in flight) SB_NST-1
+    // k-steps ahead; every lane reads back exactly the word it copied, so no barrier is needed.
+    // (the address is base + offset, rebuilt for every copy: incrementing the pointer the copy
+    // was issued with waits until the copy has read it -- measured as a long-scoreboard stall
+    // on every k-step)
+    const double* abase = c.L + ra + 2 * g;
+    int aoff = coff(tg, m);
+    int d = 4 * m - 8 - 4 * tg;                      // coff(k + 4) - coff(k); decreases by 16 per k-step
+    int ksleft = active ? J0 / 4 : 0;                // k-steps of this pass not yet issued
+    auto a_issue = [&](int stage) {
+      if (ksleft > 0) {
+        const double* src = abase + aoff;
+        if (NCT == 8) cp_async16_cg(c.ring + stage * 512, src);
+        else cp_async16_ca(c.ring + stage * 512, src);  // four warps share these rows: keep them in L1
+        aoff += d; d -= 16; ksleft--;
+      }
+      cp_async_commit();
+    };
 #pragma unroll
-  for (int s = 0; s < SB_NST - 1; s++) a_issue(s);
-#pragma unroll 1
-  for (int ch = 0; ch < c.nch; ch++) {
-    SuT tn;
-    tn.t0 = tn.t1 = make_double2(0.0, 0.0); tn.dk = tn.sk = 0.0;
-    const bool last = ch + 1 == c.nch;
-    const bool nxt = !last || more;
-    if (nxt) su_t_load(c, last ? 0 : ch + 1, first && !last, tn);
+    for (int s = 0; s < SB_NST - 1; s++) a_issue(s);
+    // one chunk: fetch T chunk g+LA into `tld`, the DMMAs of chunk g, publish chunk g+1 from `tst`
+    // (LA == 1: tst is tld itself; LA == 2: the registers filled one chunk earlier)
+    double2 an = make_double2(0.0, 0.0);             // A fragment of the next k-step (in registers)
     if (active) {
-      const uint32_t tb = smem_u32(c.T + c.buf * (SB_KCH * SB_LDT) + tg * SB_LDT + col0 + g);
+      cp_async_wait<SB_NST - 2>();
+      an = lds_f64x2(c.ring);
+    }
+    auto chunk = [&](int ch, SuT& tld, SuT& tst) {
+      const int gl = c.g + LA;                       // the chunk to fetch now
+      const bool ld = gl < c.gtot;
+      if (ld) su_t_load(c, ch + LA >= c.nch ? ch + LA - c.nch : ch + LA, c.rhs && gl < c.nch, tld);
+      if (active) {
+        const uint32_t tb = smem_u32(c.T + c.buf * (SB_KCH * SB_LDT) + tg * SB_LDT + col0 + g);
 #pragma unroll
-      for (int ks = 0; ks < SB_NST; ks++) {
-        a_issue((ks + SB_NST - 1) % SB_NST);
-        cp_async_wait<SB_NST - 1>();
-        const double2 a = lds_f64x2(c.ring + ks * 512);
+        for (int ks = 0; ks < SB_NST; ks++) {
+          a_issue((ks + SB_NST - 1) % SB_NST);
+          const double2 a = an;
+          cp_async_wait<SB_NST - 2>();               // the copy of the NEXT k-step has landed
+          an = lds_f64x2(c.ring + ((ks + 1) % SB_NST) * 512);
+          if constexpr (NCT == 2) {
+            double b0, b1;                           // (one asm: both loads in flight before the DMMAs)
+            asm volatile("ld.shared.f64 %0, [%2];\n\tld.shared.f64 %1, [%2+64];"
+                         : "=d"(b0), "=d"(b1) : "r"(tb + 8 * (ks * 4 * SB_LDT)));
+            dmma884(cx[0][0], cx[0][1], a.x, b0);
+            dmma884(cy[0][0], cy[0][1], a.y, b0);
+            dmma884(cx[1][0], cx[1][1], a.x, b1);
+            dmma884(cy[1][0], cy[1][1], a.y, b1);
+          } else {
 #pragma unroll
-        for (int h = 0; h < NCT; h += 4) {
-          double b[4];
+            for (int h = 0; h < NCT; h += 4) {
+              double b[4];
+              asm volatile("ld.shared.f64 %0, [%4];\n\tld.shared.f64 %1, [%4+64];\n\t"
+                           "ld.shared.f64 %2, [%4+128];\n\tld.shared.f64 %3, [%4+192];"
+                           : "=d"(b[0]), "=d"(b[1]), "=d"(b[2]), "=d"(b[3])
+                           : "r"(tb + 8 * (ks * 4 * SB_LDT + 8 * h)));
 #pragma unroll
-          for (int t = 0; t < 4 && h + t < NCT; t++) b[t] = lds_f64(tb + 8 * (ks * 4 * SB_LDT + 8 * (h + t)));
-#pragma unroll
-          for (int t = 0; t < 4 && h + t < NCT; t++) {
-            dmma884(cx[h + t][0], cx[h + t][1], a.x, b[t]);
-            dmma884(cy[h + t][0], cy[h + t][1], a.y, b[t]);
+              for (int t = 0; t < 4; t++) {
+                dmma884(cx[h + t][0], cx[h + t][1], a.x, b[t]);
+                dmma884(cy[h + t][0], cy[h + t][1], a.y, b[t]);
+              }
+            }
           }
         }
       }
+      if (LA == 1) {
+        if (ld) su_t_store(c, c.buf ^ 1, tld);
+      } else {
+        if (c.g + 1 < c.gtot) su_t_store(c, c.buf ^ 1, tst);
+      }
+      __syncthreads();
+      c.buf ^= 1;
+      c.g++;
+    };
+#pragma unroll 1
+    for (int ch = 0; ch < c.nch; ch += 2) {          // (nch is even: J0 is a multiple of 64)
+      if (LA == 1) {
+        SuT t;
+        t.t0 = t.t1 = make_double2(0.0, 0.0); t.dk = t.sk = 0.0;
+        chunk(ch, t, t);
+        chunk(ch + 1, t, t);
+      } else {
+        // look-ahead 2 without register copies: tn holds chunk g+1 on entry; the two register
+        // sets swap roles every chunk
+        SuT t;
+        t.t0 = t.t1 = make_double2(0.0, 0.0); t.dk = t.sk = 0.0;
+        chunk(ch, t, c.tn);                          // fetch g+2 -> t ; publish g+1 from tn
+        chunk(ch + 1, c.tn, t);                      // fetch g+3 -> tn ; publish g+2 from t
+      }
     }
-    if (nxt) su_t_store(c, c.buf ^ 1, tn);
-    __syncthreads();
-    c.buf ^= 1;
+    cp_async_wait<0>();
   }
-  cp_async_wait<0>();
   if (!active) return;
-  // epilogue: panel -= accumulators
-  if (c.nbw == SB && ra >= J0 + SB && ra + 16 <= m) {
-    // interior item: rows ra+2g, ra+2g+1 of a column are one aligned 16-byte word
+  if constexpr (NCT == 8) {
+    // ---- SU_TRSM: (panel - acc), row solve against the diagonal block, store ----
+    // (rows >= J0 + 64: every column of the super-panel exists for them)
+    long long tp = phase_begin(*c.W);
+    const bool interior = ra + 16 <= m;
+    const int r0 = ra + 2 * g;
+    const bool vx = r0 < m, vy = r0 + 1 < m;
+    if (interior) {
+#pragma unroll
+      for (int t = 0; t < 8; t++) {
+#pragma unroll
+        for (int hh = 0; hh < 2; hh++) {
+          const int col = J0 + 8 * t + 2 * tg + hh;
+          const double2 v = *reinterpret_cast<const double2*>(c.L + coff(col, m) + r0);
+          cx[t][hh] = v.x - cx[t][hh];
+          cy[t][hh] = v.y - cy[t][hh];
+        }
+      }
+    } else {
+#pragma unroll
+      for (int t = 0; t < 8; t++) {
+#pragma unroll
+        for (int hh = 0; hh < 2; hh++) {
+          const double* q = c.L + coff(J0 + 8 * t + 2 * tg + hh, m);
+          const double v0 = vx ? q[r0] : 0.0, v1 = vy ? q[r0 + 1] : 0.0;
+          cx[t][hh] = v0 - cx[t][hh];
+          cy[t][hh] = v1 - cy[t][hh];
+        }
+      }
+    }
+    int hmA = 0, hmB = 0;
+    phase_end(*c.W, 11, tp);
+    tp = phase_begin(*c.W);
+    trsm_unit(cx, cy, c.Wm, c.rinv, vx, vy, hmA, hmB, c.L, m, J0, r0, interior);
+    if (hmA > 0) atomicMax(&c.th[lane], hmA);
+    if (hmB > 0) atomicMax(&c.th[32 + lane], hmB);
+    phase_end(*c.W, 12, tp);
+  } else if (mode == SU_DIAG) {
+    // ---- diagonal block: (M - acc) into the packed nbw x nbw block in shared memory ----
+    const int nbw = c.nbw;
+#pragma unroll
+    for (int t = 0; t < NCT; t++) {
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        const int cb = col0 + 8 * t + 2 * tg + (e & 1);          // block-local column
+        const int rb = ra - J0 + 2 * g + (e >> 1);               // block-local row
+        if (cb < nbw && rb < nbw && rb >= cb) {
+          const double v = c.L[coff(J0 + cb, m) + J0 + rb];
+          const double acc = (e & 2) ? cy[t][e & 1] : cx[t][e & 1];
+          c.blk[packed_off(cb, nbw) + rb] = v - acc;
+        }
+      }
+    }
+  } else if (c.nbw == SB && ra + 16 <= m) {
+    // ---- SU_RMW, interior item: rows ra+2g, ra+2g+1 of a column are one aligned 16-byte word
     // (four loads, then four stores: read-modify-writes in program order would be
     // serialised L2 round trips)
     double* base = c.L + ra + 2 * g;
@@ -645,7 +864,7 @@ __device__ __forceinline__ void su_pass(SuCtx& c, bool active, int ra, int col0,
       }
     }
   } else {
-    // item on the diagonal block / at the ragged end: element-wise, only i >= col, i < m
+    // ---- SU_RMW at the ragged end: element-wise, only i < m ----
 #pragma unroll
     for (int t = 0; t < NCT; t++) {
       double* q[4];
@@ -667,66 +886,150 @@ __device__ __forceinline__ void su_pass(SuCtx& c, bool active, int ra, int col0,
   }
 }
 
-// fb: FB_DOUBLES of shared memory (T buffers, then the warps' A rings)
-static __device__ __noinline__ void super_update(int m, int J0, int nbw, double* L, const double* D,
-                                                 double* Sf, double* fb) {
+// start a group of K-loop passes (`npass` sweeps over the nch chunks, look-ahead LA)
+__device__ __forceinline__ void su_t_prime(SuCtx& c, int npass, int LA, bool rhs) {
+  c.g = 0; c.gtot = npass * c.nch; c.rhs = rhs;
+  SuT t;
+  su_t_load(c, 0, rhs, t);
+  su_t_store(c, c.buf, t);
+  __syncthreads();
+  if (LA == 2) su_t_load(c, 1, rhs, c.tn);           // (nch >= 2)
+}
+
+// One super-panel (columns J0 .. J0+nbw-1) of factor_ldl_big.  Returns (block-uniform) true if
+// the speculation "theta clamp inactive" could not be proven for one of its columns.
+//   1. K-loop passes of 16x16 items: the left-over row units below the diagonal block (those that
+//      do not fill a pass of sixteen 16x64 units; panel -= acc in global memory) and, in the last
+//      of these passes, the items of the diagonal block, which land in shared memory;
+//   2. the right-hand-side row (accumulated by the T-build threads) is reduced, the nbw x nbw
+//      diagonal block is factorised in shared memory by factor_panels (right-hand side riding
+//      along), written to L, and the row-solve tables Wm = D_k L11[j][k], 1/D_k are built;
+//   3. full passes of sixteen 16x64 units below the diagonal block: K-loop, then the row solve
+//      against the diagonal block in registers (trsm_unit) -- each entry of the panel is read
+//      once and written once; the left-over units of step 1 get their row solve last.
+static __device__ __noinline__ bool super_panel(int m, int J0, int nbw, Work& W, double beta, double delta,
+                                                double* Sf) {
   const int tid = threadIdx.x, lane = tid & 31, warp = warp_id();
+  double* fb = W.fb;
   SuCtx c;
   c.m = m; c.J0 = J0; c.nbw = nbw; c.nch = J0 / SB_KCH;   // (J0 is a multiple of SB)
-  c.L = L; c.D = D; c.Sf = Sf; c.T = fb;
+  c.L = W.L; c.D = W.D; c.Sf = Sf; c.T = fb; c.W = &W;
   c.ring = smem_u32(fb + FB_T + warp * SB_RING) + lane * 16;
+  c.blk = fb;                                        // (aliases T: used between the K-loop groups)
+  c.Wm = fb + FB_T + NWARP * SB_RING;
+  c.rinv = c.Wm + SB * SB_LDT;
+  c.th = reinterpret_cast<int*>(c.rinv + SB);
   c.kk = tid >> 4; c.c4 = (tid & 15) * 4;
   c.r[0] = c.r[1] = c.r[2] = c.r[3] = 0.0;
-  c.buf = 0;
-  {
-    SuT t;
-    su_t_load(c, 0, true, t);
-    su_t_store(c, 0, t);
-  }
-  __syncthreads();
-  // rows J0 .. m-1 in units of 16: the `rem` topmost units (they include the diagonal block) are
-  // cut into four 16x16 items each so that a partial pass still occupies all sixteen warps (and
-  // the items above the diagonal are skipped); the rest goes in full passes of 16x64 units
-  const int nunit = (m - J0 + 15) >> 4;
-  const int nfull = nunit >> 4, rem = nunit & 15;
-  const int nq = (rem + 3) >> 2;
-  for (int pss = 0; pss < nfull; pss++) {
-    const int ru = rem + pss * NWARP + warp;
-    su_pass<8>(c, true, J0 + 16 * ru, 0, pss == 0, pss + 1 < nfull || nq > 0);
-  }
+  c.buf = 0; c.g = c.gtot = 0; c.rhs = false;
+  c.tn.t0 = c.tn.t1 = make_double2(0.0, 0.0); c.tn.dk = c.tn.sk = 0.0;
+  const bool kloop = J0 > 0;
+  const int nbelow = (m - J0 - nbw + 15) >> 4;       // 16-row units below the diagonal block
+  const int nfull = nbelow >> 4, rem = nbelow & 15;
+  const int nru = (nbw + 15) >> 4;                   // row units of the diagonal block
+  const int ndiag = nru * (nru + 1) / 2;             // its items on or below the diagonal
+  // (the diagonal items must all sit in the LAST pass -- their epilogue overwrites the T buffers --
+  // so the left-over items are padded to a full pass when the two kinds would straddle one)
+  int nrmw = kloop ? 4 * rem : 0;
+  if ((nrmw & (NWARP - 1)) + ndiag > NWARP) nrmw = (nrmw + NWARP - 1) & ~(NWARP - 1);
+  const int nit = nrmw + ndiag;
+  const int nq = (nit + NWARP - 1) / NWARP;
+  if (tid < SB) c.th[tid] = 0;
+  long long t0 = phase_begin(W);
+  // ---- 1. 16x16 items ----
+  if (kloop) su_t_prime(c, nq, 2, true);
   for (int q = 0; q < nq; q++) {
-    const int ru = q * 4 + (warp >> 2), cg = warp & 3;
-    const bool active = ru < rem && ru >= cg && 16 * cg < nbw;
-    su_pass<2>(c, active, J0 + 16 * ru, 16 * cg, nfull == 0 && q == 0, q + 1 < nq);
+    const int it = q * NWARP + warp;
+    // item order: left-over units first, diagonal block LAST (its epilogue overwrites T)
+    const int id = it - (nit - ndiag);               // index among the diagonal items
+    int mode = SU_RMW, ru, cg;
+    bool active = it < nit && (id >= 0 || it < 4 * rem);
+    if (id >= 0) {
+      mode = SU_DIAG;
+      ru = (id >= 6) ? 3 : (id >= 3) ? 2 : (id >= 1) ? 1 : 0;
+      cg = id - ru * (ru + 1) / 2;
+    } else {
+      ru = 4 + (it >> 2);                            // (below the diagonal block: nbw == 64)
+      cg = it & 3;
+    }
+    su_pass<2>(c, mode, active, J0 + 16 * ru, 16 * cg, kloop);
   }
-  // right-hand-side row: reduce the partial sums of the 32 k-rows
-  double* part = fb;
+  __syncthreads();
+  phase_end(W, 14, t0);
+  t0 = phase_begin(W);
+  // ---- 2. right-hand-side row, diagonal block ----
+  if (kloop) {
+    double* part = fb + FB_T;                        // (the rings are idle)
 #pragma unroll
-  for (int e = 0; e < 4; e++) part[tid * 4 + e] = c.r[e];
-  __syncthreads();
-  if (tid < nbw) {
-    double sum = 0.0;
+    for (int e = 0; e < 4; e++) part[tid * 4 + e] = c.r[e];
+    __syncthreads();
+    if (tid < nbw) {
+      double sum = 0.0;
 #pragma unroll 8
-    for (int k = 0; k < SB_KCH; k++) sum += part[(k * 16 + (tid >> 2)) * 4 + (tid & 3)];
-    Sf[J0 + tid] -= sum;
+      for (int k = 0; k < SB_KCH; k++) sum += part[(k * 16 + (tid >> 2)) * 4 + (tid & 3)];
+      Sf[J0 + tid] -= sum;
+    }
+    __syncthreads();
+  }
+  bool bad;
+  {
+    Work Wb = W;
+    Wb.L = c.blk;
+    Wb.D = W.D + J0;
+    Wb.P = fb + 2176;                                // (packed_doubles(64) = 2128) scratch of 1856 doubles
+    Wb.prof = nullptr;
+    // the look-ahead factorisation (serial chain on its own warp); speculative like this sweep:
+    // a failure is reported to the caller, who redoes the whole factorisation
+    bad = factor_ldl_ahead(nbw, Wb, beta, delta, Sf + J0, Sf + J0);
+  }
+  // block -> L ; tables of the row solve
+  for (int e = tid; e < nbw * nbw; e += NT) {
+    const int jb = e / nbw, ib = e - jb * nbw;       // column jb, row ib
+    if (ib >= jb) {
+      const double l = c.blk[packed_off(jb, nbw) + ib];
+      c.L[coff(J0 + jb, m) + J0 + ib] = l;
+      if (ib > jb) c.Wm[jb * SB_LDT + ib] = l * W.D[J0 + jb];
+    }
+  }
+  if (tid < nbw) c.rinv[tid] = 1.0 / W.D[J0 + tid];
+  __syncthreads();
+  phase_end(W, 9, t0);
+  if (nbelow == 0) return bad;
+  t0 = phase_begin(W);
+  // ---- 3. 16x64 units below the diagonal block ----
+  if (kloop && nfull > 0) su_t_prime(c, nfull, 1, false);
+  for (int pss = 0; pss < nfull; pss++) {
+    const int u = rem + pss * NWARP + warp;
+    su_pass<8>(c, SU_TRSM, true, J0 + SB + 16 * u, 0, kloop);
+  }
+  if (rem > 0) {
+    if (kloop) __syncthreads();                      // (their panel entries were updated by other warps)
+    su_pass<8>(c, SU_TRSM, warp < rem, J0 + SB + 16 * warp, 0, false);
   }
   __syncthreads();
+  // ---- theta check: the columns' maxima over the rows below the block ----
+  {
+    const double inv_beta2 = 1.0 / (beta * beta);
+    bool mine = false;
+    if (tid < nbw) {
+      const double tub = __hiloint2double(c.th[tid] + 1, 0);
+      mine = !(tub * tub * inv_beta2 * 1.0000001 <= W.D[J0 + tid]);
+    }
+    bad |= __syncthreads_or(mine) != 0;
+  }
+  phase_end(W, 10, t0);
+  return bad;
 }
 
 // Sf <- (L D)^-1 rhs rides along (in place).  Requires W.fb: FB_DOUBLES of shared memory.
-static __device__ __forceinline__ void factor_ldl_big(int m, Work& W, double beta, double delta,
+// Returns true if the factorisation has to be redone by the sequential rule (factor_ldl_fast).
+static __device__ __forceinline__ bool factor_ldl_big(int m, Work& W, double beta, double delta,
                                                       const double* __restrict__ rhs, double* Sf) {
   for (int i = threadIdx.x; i < m; i += NT) Sf[i] = rhs[i];
   __syncthreads();
-  for (int J0 = 0; J0 < m; J0 += SB) {
-    const int nbw = min(SB, m - J0);
-    if (J0 > 0) {
-      const long long t0 = phase_begin(W);
-      super_update(m, J0, nbw, W.L, W.D, Sf, W.fb);
-      phase_end(W, 14, t0);
-    }
-    factor_panels(m, W, beta, delta, Sf, Sf, J0, J0 + nbw, J0);
-  }
+  bool bad = false;
+  for (int J0 = 0; J0 < m; J0 += SB) bad |= super_panel(m, J0, min(SB, m - J0), W, beta, delta, Sf);
+  return bad;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -921,8 +1224,7 @@ __device__ __forceinline__ void step1_solve(double* __restrict__ L, int m, int j
 }
 
 static __device__ __forceinline__ bool factor_ldl_ahead(int m, Work& W, double beta, double delta,
-                                                        const double* __restrict__ rhs,
-                                                        double* __restrict__ Sf) {
+                                                        const double* rhs, double* __restrict__ Sf) {
   const int tid = threadIdx.x, lane = tid & 31, warp = warp_id();
   const int g = lane >> 2, tg = lane & 3;
   double* __restrict__ L = W.L;
@@ -940,7 +1242,8 @@ static __device__ __forceinline__ bool factor_ldl_ahead(int m, Work& W, double b
   const int NOTH = NT - 32;                           // threads other than warp 0
   bool bad = false;
 
-  for (int i = tid; i < m; i += NT) Sf[i] = rhs[i];
+  if (rhs != Sf)
+    for (int i = tid; i < m; i += NT) Sf[i] = rhs[i];
   if (tid < 16) thbuf[tid] = 0;
   __syncthreads();
 

@@ -15,7 +15,7 @@ constexpr int SY_KC = 8;         // TMA-staged SYRK: packed columns per chunk
 constexpr int SY_STAGES = 3;     //   chunks in flight (ring of shared-memory stages)
 constexpr int SY_SEG = 3;        //   segments per warp per pass
 constexpr int SY_CW = 4;         //   8x8 tiles per segment
-constexpr int FB_DOUBLES = 2 * 32 * 68 + 16 * 8 * 64;   // shared memory of factor_ldl_big: two T chunks + 16 A rings
+constexpr int FB_DOUBLES = 2 * 32 * 68 + 16 * 8 * 64 + 64 * 68 + 64 + 32;   // shared memory of factor_ldl_big: two T chunks, 16 A rings, row-solve tables
 
 struct Params {
   double eps, delta, r, ldl_delta, refine_tol;
