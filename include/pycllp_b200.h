@@ -60,6 +60,21 @@ typedef struct {
   double refine_tol; /* refinement threshold ldl.cl:645           1e-8               */
   int max_iter;      /*                      primal_normal.cl:9   200                */
   int max_refine;    /* ldl.cl:645: 5 (dense); 0 (sparse, ldl.cl:698-711)            */
+  /* -- the knobs in which the reference's two implementations of this algorithm differ
+   *    (preset "cl" = pycllp/cl/*.cl, preset "py" = solvers/normal_eqns.py + _ldl.pyx) -- */
+  int nan_guard;     /* 1: NaN in dy => status 3 (normal_eqns.py:85-87); cl: 0       */
+  int carry_v;       /* iterations during which v = A'y is carried from step to step  */
+                     /* instead of recomputed (64); 0 = recompute always, the         */
+                     /* reference's operation order (primal_normal.cl:76-94,139)      */
+  int mu_mode;       /* 0: mu = delta gamma/(n+m) (primal_normal.cl:272); 1: /n (normal_eqns.py:65) */
+  int refine_mode;   /* 0: max|r| > tol, dy += solve(r) (ldl.cl:645-652);             */
+                     /* 1: max r > tol, dy -= solve(r) (_ldl.pyx:144-148)             */
+  int theta_floor;   /* 1: theta = max(0, ...) (primal_normal.cl:134); 0 (normal_eqns.py:92) */
+  int dz_mode;       /* 0: (mu - z dx)/x - z (primal_normal.cl:143); 1: (mu - x z - z dx)/x (normal_eqns.py:90) */
+  double warm_floor; /* warm starts only: x0, z0 <- max(x0, warm_floor), max(z0, warm_floor).     */
+                     /* 0 (default) = the raw end point of the previous solve, as the kernel's     */
+                     /* usage note describes (primal_normal.cl:213-219); a converged point lies on  */
+                     /* the boundary, where the method restarts badly -- ~1e-2 pulls it back inside */
 } pycllp_b200_params;
 
 #define PYCLLP_B200_OK 0
@@ -85,6 +100,11 @@ int pycllp_b200_setup_sparse(pycllp_b200_engine *e, int m, int n, const int *ind
 
 int pycllp_b200_set_params(pycllp_b200_engine *e, const pycllp_b200_params *p);
 int pycllp_b200_get_params(const pycllp_b200_engine *e, pycllp_b200_params *p);
+/* All constants of one of the reference's implementations at once: "cl" (the OpenCL
+ * kernels; the default after setup) or "py" (DensePrimalNormalSolver, normal_eqns.py:12-97:
+ * EPS 1e-8, delta 0.1, mu = delta gamma / n, refinement tolerance 1e-6 with its sign
+ * convention, no floor on theta, NaN => status 3). */
+int pycllp_b200_set_preset(pycllp_b200_engine *e, const char *name);
 
 /* Solve N <= max_problems LPs from the cold start x = z = y = 1 (cl.py:108).
  * HOST buffers: b (N, m), c (N, n) in; x (N, n), y (N, m), z (N, n), status (N),
@@ -93,12 +113,38 @@ int pycllp_b200_get_params(const pycllp_b200_engine *e, pycllp_b200_params *p);
 int pycllp_b200_solve_host(pycllp_b200_engine *e, int N, const double *b, const double *c,
                            double *x, double *y, double *z, int *status, int *iters);
 
+/* Extended form.  warm_start != 0: start from the x, z, y the PREVIOUS solve_host[_ex] call
+ * left on the device (same N) instead of x = z = y = 1 -- the repeat-solve use the library was
+ * written for (README.md:6; primal_normal.cl:213-219; cl.py:108 never enabled it).  trace
+ * (may be NULL): host buffer (N, trace_iters, 3) receiving |rho|, |sigma|, gamma of every
+ * iteration (what the kernels print at verbose > 1, primal_normal.cl:250-252); entries of
+ * iterations a problem did not reach are NaN. */
+int pycllp_b200_solve_host_ex(pycllp_b200_engine *e, int N, const double *b, const double *c,
+                              int warm_start, double *x, double *y, double *z, int *status,
+                              int *iters, double *trace, int trace_iters);
+
 /* Same with DEVICE buffers on the engine's device; work is enqueued on `stream`
  * (a cudaStream_t, NULL = the legacy default stream) and the call returns without
- * waiting. Outputs may be NULL. */
+ * waiting. Outputs may be NULL.  An engine has ONE set of scratch slots and one work
+ * counter: launches of one engine are serialised on the device even when they are issued
+ * on different streams (each launch waits for the previous one's completion event). */
 int pycllp_b200_solve_device(pycllp_b200_engine *e, int N, const double *d_b, const double *d_c,
                              double *d_x, double *d_y, double *d_z, int *d_status, int *d_iters,
                              void *stream);
+
+/* Device-buffer form that writes ONE packed record per problem, d_rec (N, 2n+m+1) doubles:
+ * [x (n) | y (m) | z (n) | status (int32), iterations (int32)] -- the unit of the multi-GPU
+ * exchange (one all-gather of the records collects everything).
+ * warm_start != 0: the records hold the x, y, z of a previous solve, which is the start. */
+int pycllp_b200_solve_device_packed(pycllp_b200_engine *e, int N, const double *d_b,
+                                    const double *d_c, double *d_rec, int warm_start, void *stream);
+
+/* Device-buffer form with a warm start (d_x0, d_z0, d_y0: all three or none; they may alias
+ * d_x, d_z, d_y) and an optional device trace buffer (N, trace_iters, 3). */
+int pycllp_b200_solve_device_ex(pycllp_b200_engine *e, int N, const double *d_b, const double *d_c,
+                                const double *d_x0, const double *d_z0, const double *d_y0,
+                                double *d_x, double *d_y, double *d_z, int *d_status, int *d_iters,
+                                double *d_trace, int trace_iters, void *stream);
 
 /* Kernel-level hook: one normal-equations solve per problem (ldl.cl:602-653 /
  * 656-712) on caller-supplied HOST state: x, z, c (N, n); y, b (N, m); out dy (N, m).
@@ -120,6 +166,18 @@ int pycllp_b200_ldl(pycllp_b200_engine *e, int N, int m, const double *AA, doubl
  * [0] rhs+norms [1] form M [2] factor [3] triangular solves [4] residual [5] step,
  * [6..15] sub-phases of the factorisation / SYRK (see ipm_factor.cuh). */
 int pycllp_b200_phase_profile(pycllp_b200_engine *e, int enable, unsigned long long *out16);
+
+/* Page-locked host memory for the layer above (the solver classes keep their result arrays in
+ * it and register lp.b / lp.c in place), so that the copies of solve_host are plain DMA:
+ * replaces the host side of cl.Buffer(COPY_HOST_PTR) / enqueue_copy (cl.py:46,99-121). */
+int pycllp_b200_host_alloc(pycllp_b200_engine *e, size_t bytes, void **out);
+int pycllp_b200_host_free(pycllp_b200_engine *e, void *p);
+int pycllp_b200_host_register(pycllp_b200_engine *e, void *p, size_t bytes);
+int pycllp_b200_host_unregister(pycllp_b200_engine *e, void *p);
+
+/* Bench aid: the FP64 tensor-core (DMMA m8n8k4) rate of this device in TFLOP/s, measured now
+ * (a loop of nothing but DMMAs on every SM; best of three after a warm-up). */
+int pycllp_b200_fp64_probe(pycllp_b200_engine *e, double *dmma_tflops);
 
 /* Introspection for the bench harness. */
 long long pycllp_b200_launch_count(const pycllp_b200_engine *e); /* kernels launched so far */

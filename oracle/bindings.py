@@ -30,6 +30,9 @@ def build(force=False):
     if have_ref_src and (force or not os.path.exists(ref_so) or
                          os.path.getmtime(ref_so) < os.path.getmtime(os.path.join(HERE, "ref_shim.c"))):
         subprocess.check_call(["make", "-C", HERE, "ref"], stdout=subprocess.DEVNULL)
+    import glob
+    if os.path.exists("/root/reference/pycllp/_ldl.pyx") and (force or not glob.glob(os.path.join(HERE, "_ref", "_ldl*.so"))):
+        subprocess.call(["make", "-C", HERE, "ref_py"], stdout=subprocess.DEVNULL)   # Oracle A (needs cython)
 
 
 def _d(a):
@@ -105,6 +108,22 @@ class Oracle(object):
                                     ctypes.byref(params) if params is not None else None,
                                     int(nthreads or os.cpu_count() or 1))
         return _Result(x=x, y=y, z=z, status=status, iters=iters, nrefs=nrefs, trace=trace)
+
+    def solve_dense_ex(self, A, b, c, start=None, params=None, nthreads=None, want_trace=False):
+        """Dense solve from a given start (x0, y0, z0) -- warm start -- and/or with the
+        (|rho|, |sigma|, gamma) of every iteration, shape (N, max_iter, 3), NaN where not reached."""
+        A, b, c = _f64(A), _f64(np.atleast_2d(b)), _f64(np.atleast_2d(c))
+        m, n = A.shape
+        N = b.shape[0]
+        p = params if params is not None else self.default_params()
+        x, y, z, status, iters, _ = _alloc(N, m, n)
+        if start is not None:
+            x[:], y[:], z[:] = start
+        it = np.full((N, p.max_iter, 3), np.nan) if want_trace else None
+        self.lib.oracle_solve_dense_ex(N, m, n, _d(A), _d(b), _d(c), _d(x), _d(y), _d(z), _i(status),
+                                       _i(iters), ctypes.byref(p), int(nthreads or os.cpu_count() or 1),
+                                       int(start is not None), _d(it))
+        return _Result(x=x, y=y, z=z, status=status, iters=iters, itrace=it)
 
     def solve_sparse(self, A, b, c, params=None, nthreads=None, structures=None):
         A, b, c = _f64(A), _f64(np.atleast_2d(b)), _f64(np.atleast_2d(c))

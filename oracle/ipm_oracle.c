@@ -270,12 +270,18 @@ static void d_step(dense_work *w, double *x, double *z, double *y, const double 
 }
 
 /* primal_normal.cl:201-284 standard_primal_normal (after initialize_xzyw, :14-28) */
-static int d_solve_one(dense_work *w, const double *b, const double *c, double *x, double *y,
-                       double *z, const oracle_params *p, int *iters, int *nrefs,
-                       double *trace) {
+/* warm != 0: start from the x, z, y passed in (the kernel's doc comment, primal_normal.cl:213-219;
+ * the reference's host code always re-initialises, cl.py:108).  itrace (may be NULL):
+ * (|rho|, |sigma|, gamma) of every iteration, what the kernel prints at verbose > 1
+ * (primal_normal.cl:250-252). */
+static int d_solve_one_ex(dense_work *w, const double *b, const double *c, double *x, double *y,
+                          double *z, const oracle_params *p, int *iters, int *nrefs,
+                          double *trace, int warm, double *itrace) {
   int m = w->m, n = w->n;
-  for (int i = 0; i < m; i++) y[i] = 1.0;
-  for (int j = 0; j < n; j++) { x[j] = 1.0; z[j] = 1.0; }
+  if (!warm) {
+    for (int i = 0; i < m; i++) y[i] = 1.0;
+    for (int j = 0; j < n; j++) { x[j] = 1.0; z[j] = 1.0; }
+  }
   int stat = 5;
   double normr0 = HUGE_VALF / 10, norms0 = HUGE_VALF / 10;
   int iter, refs = 0;
@@ -285,6 +291,7 @@ static int d_solve_one(dense_work *w, const double *b, const double *c, double *
     norms = d_dual_infeasibility(w, z, y, c, w->t);
     gamma = 0.0;
     for (int j = 0; j < n; j++) gamma += z[j] * x[j];
+    if (itrace) { itrace[3 * iter] = normr; itrace[3 * iter + 1] = norms; itrace[3 * iter + 2] = gamma; }
     if (normr < p->eps && norms < p->eps && gamma < p->eps) { stat = 0; break; }
     if (normr > 10 * normr0 && normr > p->eps) { stat = 2; break; }
     if (norms > 10 * norms0 && norms > p->eps) { stat = 4; break; }
@@ -298,6 +305,36 @@ static int d_solve_one(dense_work *w, const double *b, const double *c, double *
   if (nrefs) *nrefs = refs;
   if (trace) { trace[0] = normr; trace[1] = norms; trace[2] = gamma; }
   return stat;
+}
+
+static int d_solve_one(dense_work *w, const double *b, const double *c, double *x, double *y,
+                       double *z, const oracle_params *p, int *iters, int *nrefs,
+                       double *trace) {
+  return d_solve_one_ex(w, b, c, x, y, z, p, iters, nrefs, trace, 0, NULL);
+}
+
+/* Test hook for the warm-start / iteration-trace features of the engine: x, y, z are in/out when
+ * warm != 0; itrace is (N, max_iter, 3) or NULL. */
+int oracle_solve_dense_ex(int N, int m, int n, const double *A, const double *b, const double *c,
+                          double *x, double *y, double *z, int *status, int *iters,
+                          const oracle_params *params, int nthreads, int warm, double *itrace) {
+  oracle_params p;
+  if (params) p = *params; else oracle_default_params(&p, 0);
+  if (nthreads < 1) nthreads = 1;
+#pragma omp parallel num_threads(nthreads)
+  {
+    dense_work w;
+    dense_work_alloc(&w, m, n, A);
+#pragma omp for schedule(dynamic, 1)
+    for (int q = 0; q < N; q++) {
+      status[q] = d_solve_one_ex(&w, b + (size_t)q * m, c + (size_t)q * n, x + (size_t)q * n,
+                                 y + (size_t)q * m, z + (size_t)q * n, &p, iters ? iters + q : NULL,
+                                 NULL, NULL, warm,
+                                 itrace ? itrace + 3 * (size_t)q * p.max_iter : NULL);
+    }
+    dense_work_free(&w);
+  }
+  return 0;
 }
 
 int oracle_solve_dense(int N, int m, int n, const double *A, const double *b, const double *c,

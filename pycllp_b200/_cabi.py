@@ -23,7 +23,10 @@ EXPORTS = (
     "pycllp_b200_setup_dense", "pycllp_b200_setup_sparse", "pycllp_b200_set_params",
     "pycllp_b200_get_params", "pycllp_b200_solve_host", "pycllp_b200_solve_device",
     "pycllp_b200_solve_primal_normal", "pycllp_b200_ldl", "pycllp_b200_launch_count",
-    "pycllp_b200_info", "pycllp_b200_phase_profile",
+    "pycllp_b200_info", "pycllp_b200_phase_profile", "pycllp_b200_set_preset",
+    "pycllp_b200_solve_host_ex", "pycllp_b200_solve_device_ex", "pycllp_b200_host_alloc",
+    "pycllp_b200_host_free", "pycllp_b200_host_register", "pycllp_b200_host_unregister",
+    "pycllp_b200_solve_device_packed", "pycllp_b200_fp64_probe",
 )
 
 
@@ -31,7 +34,10 @@ class Params(ctypes.Structure):
     """Mirror of ``pycllp_b200_params``."""
     _fields_ = [("eps", ctypes.c_double), ("delta", ctypes.c_double), ("r", ctypes.c_double),
                 ("ldl_delta", ctypes.c_double), ("refine_tol", ctypes.c_double),
-                ("max_iter", ctypes.c_int), ("max_refine", ctypes.c_int)]
+                ("max_iter", ctypes.c_int), ("max_refine", ctypes.c_int),
+                ("nan_guard", ctypes.c_int), ("carry_v", ctypes.c_int), ("mu_mode", ctypes.c_int),
+                ("refine_mode", ctypes.c_int), ("theta_floor", ctypes.c_int), ("dz_mode", ctypes.c_int),
+                ("warm_floor", ctypes.c_double)]
 
 
 _lib = None
@@ -58,6 +64,16 @@ def load_library():
     lib.pycllp_b200_get_params.argtypes = [_vp, ctypes.POINTER(Params)]
     lib.pycllp_b200_solve_host.argtypes = [_vp, ctypes.c_int, _dp, _dp, _dp, _dp, _dp, _ip, _ip]
     lib.pycllp_b200_solve_device.argtypes = [_vp, ctypes.c_int] + [_vp] * 8
+    lib.pycllp_b200_set_preset.argtypes = [_vp, ctypes.c_char_p]
+    lib.pycllp_b200_solve_host_ex.argtypes = [_vp, ctypes.c_int, _dp, _dp, ctypes.c_int, _dp, _dp, _dp,
+                                              _ip, _ip, _dp, ctypes.c_int]
+    lib.pycllp_b200_solve_device_ex.argtypes = [_vp, ctypes.c_int] + [_vp] * 11 + [ctypes.c_int, _vp]
+    lib.pycllp_b200_solve_device_packed.argtypes = [_vp, ctypes.c_int, _vp, _vp, _vp, ctypes.c_int, _vp]
+    lib.pycllp_b200_fp64_probe.argtypes = [_vp, _dp]
+    lib.pycllp_b200_host_alloc.argtypes = [_vp, ctypes.c_size_t, ctypes.POINTER(_vp)]
+    lib.pycllp_b200_host_free.argtypes = [_vp, _vp]
+    lib.pycllp_b200_host_register.argtypes = [_vp, _vp, ctypes.c_size_t]
+    lib.pycllp_b200_host_unregister.argtypes = [_vp, _vp]
     lib.pycllp_b200_solve_primal_normal.argtypes = [_vp, ctypes.c_int, _dp, _dp, _dp, _dp, _dp,
                                                     ctypes.c_double, _dp]
     lib.pycllp_b200_ldl.argtypes = [_vp, ctypes.c_int, ctypes.c_int, _dp, _dp, _dp, ctypes.c_int,
@@ -96,6 +112,8 @@ class Engine(object):
         self.device = int(device)
         self.m = self.n = self.max_problems = 0
         self.sparse = False
+        self._pinned = []        # addresses from host_alloc
+        self._registered = {}    # address -> nbytes of host_register'ed caller buffers
 
     # -- plumbing ----------------------------------------------------------------
     def _check(self, rc, what):
@@ -105,8 +123,48 @@ class Engine(object):
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
+            for addr in list(self._registered):
+                self._lib.pycllp_b200_host_unregister(self._h, _vp(addr))
+            self._registered.clear()
+            for addr in self._pinned:
+                self._lib.pycllp_b200_host_free(self._h, _vp(addr))
+            self._pinned = []
             self._lib.pycllp_b200_destroy(self._h)
             self._h = _vp()
+
+    # -- page-locked host memory -----------------------------------------------------
+    def pinned_empty(self, shape, dtype=np.float64):
+        """A numpy array in page-locked host memory (owned by this engine, freed in close())."""
+        dtype = np.dtype(dtype)
+        shape = tuple(int(v) for v in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+        nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+        ptr = _vp()
+        self._check(self._lib.pycllp_b200_host_alloc(self._h, max(nbytes, 1), ctypes.byref(ptr)),
+                    "pycllp_b200_host_alloc")
+        self._pinned.append(ptr.value)
+        buf = (ctypes.c_char * max(nbytes, 1)).from_address(ptr.value)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape, dtype=np.int64))).reshape(shape)
+
+    def pin_in_place(self, arr):
+        """Page-lock a caller's C-contiguous array where it lies (cached; returns False when the
+        driver refuses, in which case the copies simply stay pageable)."""
+        addr, nbytes = arr.ctypes.data, arr.nbytes
+        if nbytes == 0:
+            return False
+        if self._registered.get(addr, 0) >= nbytes:
+            return True
+        if addr in self._registered:
+            self._lib.pycllp_b200_host_unregister(self._h, _vp(addr))
+            del self._registered[addr]
+        if self._lib.pycllp_b200_host_register(self._h, _vp(addr), nbytes) != 0:
+            return False
+        self._registered[addr] = nbytes
+        return True
+
+    def unpin_all(self):
+        for addr in list(self._registered):
+            self._lib.pycllp_b200_host_unregister(self._h, _vp(addr))
+        self._registered.clear()
 
     def __del__(self):
         try:
@@ -140,6 +198,10 @@ class Engine(object):
         self._check(self._lib.pycllp_b200_get_params(self._h, ctypes.byref(p)), "get_params")
         return p
 
+    def set_preset(self, name):
+        """'cl' (the OpenCL kernels' constants, default) or 'py' (solvers/normal_eqns.py)."""
+        self._check(self._lib.pycllp_b200_set_preset(self._h, name.encode()), "pycllp_b200_set_preset")
+
     def set_params(self, **kw):
         p = self.get_params()
         for k, v in kw.items():
@@ -149,21 +211,30 @@ class Engine(object):
         self._check(self._lib.pycllp_b200_set_params(self._h, ctypes.byref(p)), "set_params")
 
     # -- solve ----------------------------------------------------------------------
-    def solve_host(self, b, c, want_yz=True):
-        """b (N, m), c (N, n) numpy -> dict(x, y, z, status, iters) numpy."""
+    def solve_host(self, b, c, want_yz=True, warm_start=False, trace_iters=0, out=None):
+        """b (N, m), c (N, n) numpy -> dict(x, y, z, status, iters[, trace]) numpy.
+
+        warm_start: begin from the x, y, z the previous solve left on the device (same N).
+        trace_iters > 0: also ``trace`` (N, trace_iters, 3) = |rho|, |sigma|, gamma per iteration.
+        out: dict of preallocated result arrays (e.g. pinned) to fill instead of new ones."""
         b, c = _f64(np.atleast_2d(b)), _f64(np.atleast_2d(c))
         N = b.shape[0]
         if b.shape != (N, self.m) or c.shape != (N, self.n):
             raise ValueError("b must be (N, %d) and c (N, %d)" % (self.m, self.n))
-        x = np.empty((N, self.n))
-        y = np.empty((N, self.m)) if want_yz else None
-        z = np.empty((N, self.n)) if want_yz else None
-        status = np.empty(N, dtype=np.int32)
-        iters = np.empty(N, dtype=np.int32)
-        self._check(self._lib.pycllp_b200_solve_host(self._h, N, _d(b), _d(c), _d(x), _d(y), _d(z),
-                                                     _i(status), _i(iters)),
-                    "pycllp_b200_solve_host")
-        return dict(x=x, y=y, z=z, status=status, iters=iters)
+        out = out or {}
+        x = out.get("x") if out.get("x") is not None else np.empty((N, self.n))
+        y = out.get("y") if out.get("y") is not None else (np.empty((N, self.m)) if want_yz else None)
+        z = out.get("z") if out.get("z") is not None else (np.empty((N, self.n)) if want_yz else None)
+        status = out.get("status") if out.get("status") is not None else np.empty(N, dtype=np.int32)
+        iters = out.get("iters") if out.get("iters") is not None else np.empty(N, dtype=np.int32)
+        trace = np.empty((N, int(trace_iters), 3)) if trace_iters else None
+        self._check(self._lib.pycllp_b200_solve_host_ex(
+            self._h, N, _d(b), _d(c), int(bool(warm_start)), _d(x), _d(y), _d(z), _i(status), _i(iters),
+            _d(trace), int(trace_iters)), "pycllp_b200_solve_host_ex")
+        res = dict(x=x, y=y, z=z, status=status, iters=iters)
+        if trace is not None:
+            res["trace"] = trace
+        return res
 
     def solve_host_into(self, N, b, c, x, y, z, status, iters):
         """Raw-pointer variant for pinned buffers: every argument is an int address or None."""
@@ -178,6 +249,25 @@ class Engine(object):
             self._h, int(N), _vp(d_b), _vp(d_c), _vp(d_x or None), _vp(d_y or None),
             _vp(d_z or None), _vp(d_status or None), _vp(d_iters or None), _vp(stream or None)),
             "pycllp_b200_solve_device")
+
+    def solve_device_ex(self, N, d_b, d_c, d_x0=0, d_z0=0, d_y0=0, d_x=0, d_y=0, d_z=0, d_status=0,
+                        d_iters=0, d_trace=0, trace_iters=0, stream=0):
+        """Device pointers; x0/z0/y0 (all or none) give a warm start and may alias the outputs."""
+        v = lambda p: _vp(p or None)
+        self._check(self._lib.pycllp_b200_solve_device_ex(
+            self._h, int(N), v(d_b), v(d_c), v(d_x0), v(d_z0), v(d_y0), v(d_x), v(d_y), v(d_z),
+            v(d_status), v(d_iters), v(d_trace), int(trace_iters), v(stream)),
+            "pycllp_b200_solve_device_ex")
+
+    def solve_device_packed(self, N, d_b, d_c, d_rec, stream=0, warm_start=False):
+        """One record per problem, (N, 2n+m+1) float64: x | y | z | (status, iterations as int32)."""
+        self._check(self._lib.pycllp_b200_solve_device_packed(
+            self._h, int(N), _vp(d_b), _vp(d_c), _vp(d_rec), int(bool(warm_start)), _vp(stream or None)),
+            "pycllp_b200_solve_device_packed")
+
+    @property
+    def record_width(self):
+        return 2 * self.n + self.m + 1
 
     # -- kernel-level hooks -------------------------------------------------------------
     def solve_primal_normal(self, x, z, y, b, c, mu):
@@ -205,6 +295,12 @@ class Engine(object):
         names = ("rhs_norms", "form_M", "factor", "tri_solve", "residual", "step",
                  "f_copy", "f_waitEd", "f_blockrow", "f_diag", "f_solve", "f_table", "f_waitE3", "f_old", "f_waitEb", "f_update")
         return {k: int(out[i]) for i, k in enumerate(names)}
+
+    def fp64_probe(self):
+        """FP64 tensor-core (DMMA) TFLOP/s of this device, measured now."""
+        v = ctypes.c_double()
+        self._check(self._lib.pycllp_b200_fp64_probe(self._h, ctypes.byref(v)), "pycllp_b200_fp64_probe")
+        return float(v.value)
 
     # -- introspection ---------------------------------------------------------------------
     @property

@@ -1,7 +1,10 @@
 // cabi.cu -- the C ABI declared in include/pycllp_b200.h (engine object, setup-time
 // analysis of the shared matrix, host/device solve entry points, test hooks).
 #include <algorithm>
+#include <climits>
+#include <cmath>
 #include <cstdio>
+#include <exception>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -29,6 +32,13 @@ struct pycllp_b200_engine {
   double *d_b = nullptr, *d_c = nullptr, *d_x = nullptr, *d_y = nullptr, *d_z = nullptr;
   int *d_status = nullptr, *d_iters = nullptr;
   cudaStream_t stream = nullptr;
+  cudaEvent_t last_done = nullptr;    // completion of the most recent launch (any stream)
+  bool launched = false;
+  int resident = 0;                   // problems whose x, y, z the staging buffers hold (warm start)
+  double* d_trace = nullptr;
+  size_t trace_cap = 0;               // doubles
+  double* d_dy = nullptr;             // output of the solve_primal_normal hook
+  size_t dy_cap = 0;
   long long launches = 0;
   unsigned long long* d_prof = nullptr;   // phase counters (debug/profiling aid)
 };
@@ -69,6 +79,42 @@ void default_params(Params& p, bool sparse) {
   p.refine_tol = 1e-8;          // ldl.cl:645
   p.max_iter = 200;             // primal_normal.cl:9
   p.max_refine = sparse ? 0 : 5;  // ldl.cl:645 / ldl.cl:698-711 (commented out)
+  p.nan_guard = 0;              // the kernels have no NaN test
+  p.carry_v = 64;
+  p.mu_mode = 0;                // :272
+  p.refine_mode = 0;            // ldl.cl:645-652
+  p.theta_floor = 1;            // primal_normal.cl:134
+  p.dz_mode = 0;                // :143
+  p.warm_floor = 0.0;           // :213-219: "begin from the position the previous call ended in"
+}
+
+// solvers/normal_eqns.py + _ldl.pyx
+void python_params(Params& p, bool sparse) {
+  default_params(p, sparse);
+  p.eps = 1.0e-8;               // normal_eqns.py:12
+  p.delta = 0.1;                // :52
+  p.refine_tol = 1e-6;          // _ldl.pyx:132
+  p.max_refine = 5;             // _ldl.pyx:144
+  p.nan_guard = 1;              // normal_eqns.py:85-87
+  p.mu_mode = 1;                // :65
+  p.refine_mode = 1;            // _ldl.pyx:144-148
+  p.theta_floor = 0;            // normal_eqns.py:92
+  p.dz_mode = 1;                // :90
+}
+
+// Run an API body; C++ exceptions (bad_alloc, length_error from the setup-time vectors) must
+// not cross the C boundary.
+template <class F>
+int guarded(pycllp_b200_engine* e, F&& body) {
+  try {
+    return body();
+  } catch (const std::bad_alloc&) {
+    return fail(e, PYCLLP_B200_ERR_ARG, "out of host memory");
+  } catch (const std::exception& ex) {
+    return fail(e, PYCLLP_B200_ERR_ARG, std::string("invalid argument: ") + ex.what());
+  } catch (...) {
+    return fail(e, PYCLLP_B200_ERR_ARG, "unknown C++ exception");
+  }
 }
 
 template <class T>
@@ -90,6 +136,11 @@ void free_matrix(pycllp_b200_engine* e) {
     if (p) cudaFree(p);
   e->d_b = e->d_c = e->d_x = e->d_y = e->d_z = nullptr;
   e->d_status = e->d_iters = nullptr;
+  if (e->d_trace) cudaFree(e->d_trace);
+  if (e->d_dy) cudaFree(e->d_dy);
+  e->d_trace = e->d_dy = nullptr;
+  e->trace_cap = e->dy_cap = 0;
+  e->resident = 0;
   e->d_prof = nullptr;
   e->sc.prof = nullptr;
   e->ready = false;
@@ -146,9 +197,14 @@ int finish_setup(pycllp_b200_engine* e, int max_problems) {
 }
 
 int run(pycllp_b200_engine* e, Batch& B, cudaStream_t stream) {
+  // one work counter and one set of scratch slots per engine: a launch may not start (not even
+  // its counter reset) before the previous one, on whatever stream, has finished
+  if (e->launched) CU(cudaStreamWaitEvent(stream, e->last_done, 0));
   CU(cudaMemsetAsync(e->sc.counter, 0, sizeof(int), stream));
   int grid = std::min(e->grid, std::max(1, B.N));
   CU(launch_solve(e->A, B, e->sc, e->p, grid, e->smem_bytes, stream));
+  CU(cudaEventRecord(e->last_done, stream));
+  e->launched = true;
   e->launches += 1;
   return 0;
 }
@@ -184,6 +240,7 @@ int pycllp_b200_create(int device, pycllp_b200_engine** out) {
   cudaDeviceProp prop;
   err = cudaGetDeviceProperties(&prop, device);
   if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+  if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e->last_done, cudaEventDisableTiming);
   if (err != cudaSuccess) {
     g_create_error = cudaGetErrorString(err);
     delete e;
@@ -203,15 +260,13 @@ int pycllp_b200_destroy(pycllp_b200_engine* e) {
     cudaDeviceSynchronize();
     free_matrix(e);
     if (e->stream) cudaStreamDestroy(e->stream);
+    if (e->last_done) cudaEventDestroy(e->last_done);
   }
   delete e;
   return 0;
 }
 
-int pycllp_b200_setup_dense(pycllp_b200_engine* e, int m, int n, const double* A,
-                            int max_problems) {
-  if (!e || !A || m <= 0 || n <= 0 || max_problems <= 0)
-    return fail(e, PYCLLP_B200_ERR_ARG, "setup_dense: bad argument");
+static int setup_dense_impl(pycllp_b200_engine* e, int m, int n, const double* A, int max_problems) {
   DeviceGuard guard(e->device);
   free_matrix(e);
   Matrix& M = e->A;
@@ -251,7 +306,6 @@ int pycllp_b200_setup_dense(pycllp_b200_engine* e, int m, int n, const double* A
     sptr[i + 1] = (int)scol.size();
   }
   for (int k = 0; k < M.nd; k++) colrow[dcols[k]] = -2;
-  std::vector<double> Ah(A, A + (size_t)m * n);
   // TMA-staged SYRK operand: chunks of SY_KC packed columns, k-major, rows padded to ldm
   // with ldm = 4 (mod 16) so that the four k-rows of a DMMA fragment hit disjoint banks
   int ldm = (m + 7) / 8 * 8;
@@ -286,7 +340,6 @@ int pycllp_b200_setup_dense(pycllp_b200_engine* e, int m, int n, const double* A
   }
   int rc;
   if ((rc = upload(e, Apk, &M.sy_A))) return rc;
-  if ((rc = upload(e, Ah, &M.A))) return rc;
   if ((rc = upload(e, Ad, &M.Ad))) return rc;
   if ((rc = upload(e, dcols, &M.dcols))) return rc;
   if ((rc = upload(e, sptr, &M.sing_ptr))) return rc;
@@ -298,10 +351,22 @@ int pycllp_b200_setup_dense(pycllp_b200_engine* e, int m, int n, const double* A
   return finish_setup(e, max_problems);
 }
 
-int pycllp_b200_setup_sparse(pycllp_b200_engine* e, int m, int n, const int* indptr,
+int pycllp_b200_setup_dense(pycllp_b200_engine* e, int m, int n, const double* A,
+                            int max_problems) {
+  if (!e || !A || m <= 0 || n <= 0 || max_problems <= 0)
+    return fail(e, PYCLLP_B200_ERR_ARG, "setup_dense: bad argument");
+  if ((long long)m * (m + 1) / 2 + m > (long long)INT_MAX / 2)
+    return fail(e, PYCLLP_B200_ERR_ARG, "setup_dense: m too large for 32-bit factor offsets");
+  return guarded(e, [&] { return setup_dense_impl(e, m, n, A, max_problems); });
+}
+
+static int setup_sparse_impl(pycllp_b200_engine* e, int m, int n, const int* indptr,
                              const int* indices, const double* data, int max_problems) {
-  if (!e || !indptr || !indices || !data || m <= 0 || n <= 0 || max_problems <= 0)
-    return fail(e, PYCLLP_B200_ERR_ARG, "setup_sparse: bad argument");
+  // indptr comes from the caller: it must be a CSR row pointer before anything is sized from it
+  if (indptr[0] != 0) return fail(e, PYCLLP_B200_ERR_ARG, "setup_sparse: indptr[0] != 0");
+  for (int i = 0; i < m; i++)
+    if (indptr[i + 1] < indptr[i])
+      return fail(e, PYCLLP_B200_ERR_ARG, "setup_sparse: indptr is not non-decreasing");
   DeviceGuard guard(e->device);
   free_matrix(e);
   Matrix& M = e->A;
@@ -331,6 +396,18 @@ int pycllp_b200_setup_sparse(pycllp_b200_engine* e, int m, int n, const int* ind
   // symbolic analysis of M = A diag(d) A' (shared pattern): triples (i >= j, k, A_ik A_jk)
   struct Tr { int i, j, k; double w; };
   std::vector<Tr> tr;
+  {
+    size_t ntr = 0;                                  // sum over columns of c_k (c_k + 1) / 2
+    for (int k = 0; k < n; k++) {
+      const size_t ck = (size_t)(Tp[k + 1] - Tp[k]);
+      ntr += ck * (ck + 1) / 2;
+    }
+    if (ntr > (size_t)INT_MAX)
+      return fail(e, PYCLLP_B200_ERR_ARG,
+                  "setup_sparse: the pattern of A A' has more than 2^31 terms (A too dense for the "
+                  "sparse path: use setup_dense)");
+    tr.reserve(ntr);
+  }
   for (int k = 0; k < n; k++)
     for (int a = Tp[k]; a < Tp[k + 1]; a++)
       for (int b2 = Tp[k]; b2 <= a; b2++)
@@ -368,12 +445,34 @@ int pycllp_b200_setup_sparse(pycllp_b200_engine* e, int m, int n, const int* ind
   return finish_setup(e, max_problems);
 }
 
+int pycllp_b200_setup_sparse(pycllp_b200_engine* e, int m, int n, const int* indptr,
+                             const int* indices, const double* data, int max_problems) {
+  if (!e || !indptr || !indices || !data || m <= 0 || n <= 0 || max_problems <= 0)
+    return fail(e, PYCLLP_B200_ERR_ARG, "setup_sparse: bad argument");
+  if ((long long)m * (m + 1) / 2 + m > (long long)INT_MAX / 2)
+    return fail(e, PYCLLP_B200_ERR_ARG, "setup_sparse: m too large for 32-bit factor offsets");
+  return guarded(e, [&] { return setup_sparse_impl(e, m, n, indptr, indices, data, max_problems); });
+}
+
 int pycllp_b200_set_params(pycllp_b200_engine* e, const pycllp_b200_params* p) {
   if (!e || !p) return fail(e, PYCLLP_B200_ERR_ARG, "set_params: null argument");
   if (p->max_iter < 0 || p->max_refine < 0 || !(p->r > 0))
     return fail(e, PYCLLP_B200_ERR_ARG, "set_params: invalid value");
   e->p.eps = p->eps; e->p.delta = p->delta; e->p.r = p->r; e->p.ldl_delta = p->ldl_delta;
   e->p.refine_tol = p->refine_tol; e->p.max_iter = p->max_iter; e->p.max_refine = p->max_refine;
+  e->p.nan_guard = p->nan_guard != 0; e->p.carry_v = p->carry_v < 0 ? 0 : p->carry_v;
+  e->p.mu_mode = p->mu_mode != 0; e->p.refine_mode = p->refine_mode != 0;
+  e->p.theta_floor = p->theta_floor != 0; e->p.dz_mode = p->dz_mode != 0;
+  e->p.warm_floor = p->warm_floor > 0 ? p->warm_floor : 0.0;
+  return 0;
+}
+
+int pycllp_b200_set_preset(pycllp_b200_engine* e, const char* name) {
+  if (!e || !name) return fail(e, PYCLLP_B200_ERR_ARG, "set_preset: null argument");
+  if (!e->ready) return fail(e, PYCLLP_B200_ERR_STATE, "set_preset: call setup_dense/setup_sparse first");
+  if (!strcmp(name, "cl")) default_params(e->p, e->A.sparse != 0);
+  else if (!strcmp(name, "py")) python_params(e->p, e->A.sparse != 0);
+  else return fail(e, PYCLLP_B200_ERR_ARG, "set_preset: unknown preset (cl, py)");
   return 0;
 }
 
@@ -381,38 +480,90 @@ int pycllp_b200_get_params(const pycllp_b200_engine* e, pycllp_b200_params* p) {
   if (!e || !p) return PYCLLP_B200_ERR_ARG;
   p->eps = e->p.eps; p->delta = e->p.delta; p->r = e->p.r; p->ldl_delta = e->p.ldl_delta;
   p->refine_tol = e->p.refine_tol; p->max_iter = e->p.max_iter; p->max_refine = e->p.max_refine;
+  p->nan_guard = e->p.nan_guard; p->carry_v = e->p.carry_v; p->mu_mode = e->p.mu_mode;
+  p->refine_mode = e->p.refine_mode; p->theta_floor = e->p.theta_floor; p->dz_mode = e->p.dz_mode;
+  p->warm_floor = e->p.warm_floor;
   return 0;
 }
 
-int pycllp_b200_solve_device(pycllp_b200_engine* e, int N, const double* d_b, const double* d_c,
-                             double* d_x, double* d_y, double* d_z, int* d_status, int* d_iters,
-                             void* stream) {
+int pycllp_b200_solve_device_ex(pycllp_b200_engine* e, int N, const double* d_b, const double* d_c,
+                                const double* d_x0, const double* d_z0, const double* d_y0,
+                                double* d_x, double* d_y, double* d_z, int* d_status, int* d_iters,
+                                double* d_trace, int trace_iters, void* stream) {
   if (!e) return PYCLLP_B200_ERR_ARG;
   if (!e->ready) return fail(e, PYCLLP_B200_ERR_STATE, "solve: call setup_dense/setup_sparse first");
   if (N < 0 || !d_b || !d_c) return fail(e, PYCLLP_B200_ERR_ARG, "solve: bad argument");
+  const int nstart = (d_x0 != nullptr) + (d_z0 != nullptr) + (d_y0 != nullptr);
+  if (nstart != 0 && nstart != 3)
+    return fail(e, PYCLLP_B200_ERR_ARG, "solve: a warm start needs x0, z0 and y0");
+  if (d_trace && trace_iters <= 0) return fail(e, PYCLLP_B200_ERR_ARG, "solve: trace_iters <= 0");
   if (N == 0) return 0;
   DeviceGuard guard(e->device);
   Batch B{};
   B.N = N; B.b = d_b; B.c = d_c; B.x = d_x; B.y = d_y; B.z = d_z;
   B.status = d_status; B.iters = d_iters;
+  B.warm = nstart == 3; B.x0 = d_x0; B.z0 = d_z0; B.y0 = d_y0;
+  B.trace = d_trace; B.trace_iters = d_trace ? trace_iters : 0;
   return run(e, B, (cudaStream_t)stream);
 }
 
-int pycllp_b200_solve_host(pycllp_b200_engine* e, int N, const double* b, const double* c,
-                           double* x, double* y, double* z, int* status, int* iters) {
+int pycllp_b200_solve_device_packed(pycllp_b200_engine* e, int N, const double* d_b,
+                                    const double* d_c, double* d_rec, int warm_start, void* stream) {
+  if (!e) return PYCLLP_B200_ERR_ARG;
+  if (!e->ready) return fail(e, PYCLLP_B200_ERR_STATE, "solve: call setup_dense/setup_sparse first");
+  if (N < 0 || !d_b || !d_c || !d_rec) return fail(e, PYCLLP_B200_ERR_ARG, "solve: bad argument");
+  if (N == 0) return 0;
+  DeviceGuard guard(e->device);
+  const size_t m = e->A.m, n = e->A.n, ld = 2 * n + m + 1;
+  Batch B{};
+  B.N = N; B.b = d_b; B.c = d_c;
+  B.x = d_rec; B.y = d_rec + n; B.z = d_rec + n + m;
+  B.status = reinterpret_cast<int*>(d_rec + 2 * n + m);
+  B.iters = B.status + 1;
+  B.ld_x = B.ld_y = B.ld_z = ld;
+  B.ld_s = (int)(2 * ld);
+  if (warm_start) { B.warm = 1; B.x0 = B.x; B.y0 = B.y; B.z0 = B.z; B.ld_0 = ld; }
+  return run(e, B, (cudaStream_t)stream);
+}
+
+int pycllp_b200_solve_device(pycllp_b200_engine* e, int N, const double* d_b, const double* d_c,
+                             double* d_x, double* d_y, double* d_z, int* d_status, int* d_iters,
+                             void* stream) {
+  return pycllp_b200_solve_device_ex(e, N, d_b, d_c, nullptr, nullptr, nullptr, d_x, d_y, d_z, d_status,
+                                     d_iters, nullptr, 0, stream);
+}
+
+int pycllp_b200_solve_host_ex(pycllp_b200_engine* e, int N, const double* b, const double* c,
+                              int warm_start, double* x, double* y, double* z, int* status,
+                              int* iters, double* trace, int trace_iters) {
   if (!e) return PYCLLP_B200_ERR_ARG;
   if (!e->ready) return fail(e, PYCLLP_B200_ERR_STATE, "solve: call setup_dense/setup_sparse first");
   if (N < 0 || N > e->max_problems || !b || !c)
     return fail(e, PYCLLP_B200_ERR_ARG, "solve: bad argument (N > max_problems?)");
+  if (warm_start && e->resident != N)
+    return fail(e, PYCLLP_B200_ERR_STATE,
+                "solve: warm start needs the x, y, z of a previous solve of the same N problems");
+  if (trace && trace_iters <= 0) return fail(e, PYCLLP_B200_ERR_ARG, "solve: trace_iters <= 0");
   if (N == 0) return 0;
   DeviceGuard guard(e->device);
   const size_t m = e->A.m, n = e->A.n;
   cudaStream_t s = e->stream;
+  const size_t tdoubles = trace ? (size_t)N * trace_iters * 3 : 0;
+  if (tdoubles > e->trace_cap) {
+    if (e->d_trace) CU(cudaFree(e->d_trace));
+    e->d_trace = nullptr; e->trace_cap = 0;
+    CU(cudaMalloc(&e->d_trace, tdoubles * sizeof(double)));
+    e->trace_cap = tdoubles;
+  }
+  if (trace) CU(cudaMemsetAsync(e->d_trace, 0xff, tdoubles * sizeof(double), s));   // all-ones = NaN
   CU(cudaMemcpyAsync(e->d_b, b, N * m * sizeof(double), cudaMemcpyHostToDevice, s));
   CU(cudaMemcpyAsync(e->d_c, c, N * n * sizeof(double), cudaMemcpyHostToDevice, s));
   Batch B{};
   B.N = N; B.b = e->d_b; B.c = e->d_c; B.x = e->d_x; B.y = e->d_y; B.z = e->d_z;
   B.status = e->d_status; B.iters = e->d_iters;
+  if (warm_start) { B.warm = 1; B.x0 = e->d_x; B.z0 = e->d_z; B.y0 = e->d_y; }
+  if (trace) { B.trace = e->d_trace; B.trace_iters = trace_iters; }
+  e->resident = 0;
   int rc = run(e, B, s);
   if (rc) return rc;
   if (x) CU(cudaMemcpyAsync(x, e->d_x, N * n * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -420,8 +571,15 @@ int pycllp_b200_solve_host(pycllp_b200_engine* e, int N, const double* b, const 
   if (z) CU(cudaMemcpyAsync(z, e->d_z, N * n * sizeof(double), cudaMemcpyDeviceToHost, s));
   if (status) CU(cudaMemcpyAsync(status, e->d_status, N * sizeof(int), cudaMemcpyDeviceToHost, s));
   if (iters) CU(cudaMemcpyAsync(iters, e->d_iters, N * sizeof(int), cudaMemcpyDeviceToHost, s));
+  if (trace) CU(cudaMemcpyAsync(trace, e->d_trace, tdoubles * sizeof(double), cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
+  e->resident = N;
   return 0;
+}
+
+int pycllp_b200_solve_host(pycllp_b200_engine* e, int N, const double* b, const double* c,
+                           double* x, double* y, double* z, int* status, int* iters) {
+  return pycllp_b200_solve_host_ex(e, N, b, c, 0, x, y, z, status, iters, nullptr, 0);
 }
 
 int pycllp_b200_solve_primal_normal(pycllp_b200_engine* e, int N, const double* x,
@@ -434,9 +592,14 @@ int pycllp_b200_solve_primal_normal(pycllp_b200_engine* e, int N, const double* 
   DeviceGuard guard(e->device);
   const size_t m = e->A.m, n = e->A.n;
   cudaStream_t s = e->stream;
-  // staging: d_b <- b, d_c <- c, d_x <- x, d_z <- z, d_y <- y ; dy comes back through d_status? no:
-  double* d_dy = nullptr;
-  CU(cudaMalloc(&d_dy, N * m * sizeof(double)));
+  e->resident = 0;                                   // (the staging buffers are reused below)
+  if ((size_t)N * m > e->dy_cap) {
+    if (e->d_dy) CU(cudaFree(e->d_dy));
+    e->d_dy = nullptr; e->dy_cap = 0;
+    CU(cudaMalloc(&e->d_dy, (size_t)N * m * sizeof(double)));
+    e->dy_cap = (size_t)N * m;
+  }
+  double* d_dy = e->d_dy;
   cudaError_t err = cudaSuccess;
   auto cp = [&](void* d, const void* h, size_t bytes) {
     if (err == cudaSuccess) err = cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, s);
@@ -456,7 +619,6 @@ int pycllp_b200_solve_primal_normal(pycllp_b200_engine* e, int N, const double* 
     if (!rc && err == cudaSuccess) err = cudaStreamSynchronize(s);
   }
   cudaStreamSynchronize(s);
-  cudaFree(d_dy);
   if (rc) return rc;
   if (err != cudaSuccess) return fail(e, PYCLLP_B200_ERR_CUDA, cudaGetErrorString(err));
   return 0;
@@ -512,6 +674,64 @@ int pycllp_b200_phase_profile(pycllp_b200_engine* e, int enable, unsigned long l
   }
   if (e->d_prof) CU(cudaMemset(e->d_prof, 0, bytes));
   e->sc.prof = enable ? e->d_prof : nullptr;
+  return 0;
+}
+
+// Page-locked host memory for the plugin layer: with pageable buffers every cudaMemcpyAsync of
+// solve_host goes through the driver's staging copy (the reference's pyopencl path has the same
+// cost, cl.py:99-121); pinned in place the copies are plain DMA.
+int pycllp_b200_host_alloc(pycllp_b200_engine* e, size_t bytes, void** out) {
+  if (!e || !out) return PYCLLP_B200_ERR_ARG;
+  DeviceGuard guard(e->device);
+  *out = nullptr;
+  CU(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+  return 0;
+}
+int pycllp_b200_host_free(pycllp_b200_engine* e, void* p) {
+  if (!e) return PYCLLP_B200_ERR_ARG;
+  DeviceGuard guard(e->device);
+  if (p) CU(cudaFreeHost(p));
+  return 0;
+}
+int pycllp_b200_host_register(pycllp_b200_engine* e, void* p, size_t bytes) {
+  if (!e || !p || !bytes) return PYCLLP_B200_ERR_ARG;
+  DeviceGuard guard(e->device);
+  CU(cudaHostRegister(p, bytes, cudaHostRegisterDefault));
+  return 0;
+}
+int pycllp_b200_host_unregister(pycllp_b200_engine* e, void* p) {
+  if (!e || !p) return PYCLLP_B200_ERR_ARG;
+  DeviceGuard guard(e->device);
+  CU(cudaHostUnregister(p));
+  return 0;
+}
+
+int pycllp_b200_fp64_probe(pycllp_b200_engine* e, double* dmma_tflops) {
+  if (!e || !dmma_tflops) return PYCLLP_B200_ERR_ARG;
+  DeviceGuard guard(e->device);
+  const int blocks = e->num_sms, iters = 20000;
+  double* out = nullptr;
+  CU(cudaMalloc(&out, sizeof(double) * (size_t)blocks * NT));
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  cudaError_t err = cudaEventCreate(&e0);
+  if (err == cudaSuccess) err = cudaEventCreate(&e1);
+  float best = 0.f;
+  for (int rep = 0; rep < 4 && err == cudaSuccess; rep++) {          // rep 0 = warm-up
+    err = cudaEventRecord(e0, e->stream);
+    if (err == cudaSuccess) err = launch_fp64_probe(out, blocks, iters, e->stream);
+    if (err == cudaSuccess) err = cudaEventRecord(e1, e->stream);
+    if (err == cudaSuccess) err = cudaEventSynchronize(e1);
+    float ms = 0.f;
+    if (err == cudaSuccess) err = cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && (best == 0.f || ms < best)) best = ms;
+  }
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  cudaFree(out);
+  if (err != cudaSuccess) return fail(e, PYCLLP_B200_ERR_CUDA, cudaGetErrorString(err));
+  // 8 tiles x (8 x 8 x 4 MACs) x 2 flops per warp and iteration
+  const double flops = 2.0 * 256 * 8 * (double)iters * (NT / 32) * blocks;
+  *dmma_tflops = flops / (best * 1e-3) / 1e12;
   return 0;
 }
 

@@ -69,6 +69,20 @@ __device__ __forceinline__ double block_max(double v, double* red) {
   return __shfl_sync(0xffffffffu, r, 0);     // provably warp-uniform
 }
 
+// minimum over the block of values of any sign (used as max = -min(-v))
+__device__ __forceinline__ double block_max_signed(double negv, double* red) {
+  const int lane = threadIdx.x & 31, warp = warp_id();
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) negv = fmin(negv, __shfl_xor_sync(0xffffffffu, negv, o));
+  if (lane == 0) red[warp] = negv;
+  __syncthreads();
+  double r = (lane < NWARP) ? red[lane] : INFINITY;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) r = fmin(r, __shfl_xor_sync(0xffffffffu, r, o));
+  __syncthreads();
+  return __shfl_sync(0xffffffffu, r, 0);
+}
+
 // packed lower triangle, COLUMN-major: column j holds rows j..m-1 contiguously, so that a
 // "thread per row" sweep over a column is a unit-stride access.
 // (valid while the packed size fits 31 bits; layout: packed_off in ipm_types.h)
@@ -470,7 +484,7 @@ namespace pb200 {
 
 // S = RHS - M dy ; returns max |S|   (ldl.cl:577-599); M is the block's full symmetric copy
 // in its L2-resident scratch slot, eight rows per warp at a time.
-static __device__ __forceinline__ double residual_M(int m, Work& W) {
+static __device__ __forceinline__ double residual_M(int m, Work& W, bool signed_max = false) {
   const int lane = threadIdx.x & 31, warp = warp_id();
   const int q = (lane >> 2) & 7;
   double mx = 0.0;
@@ -491,9 +505,11 @@ static __device__ __forceinline__ double residual_M(int m, Work& W) {
     if ((lane & 3) == 0 && i0 + q < m) {
       const double res = W.RHS[i0 + q] - t;
       W.S[i0 + q] = res;
-      mx = fmax(mx, fabs(res));
+      mx = fmax(mx, signed_max ? res : fabs(res));
     }
   }
+  // (signed: _ldl.pyx:144 tests np.max(r); a maximum below zero never passes a positive
+  // tolerance, so flooring it at 0 changes nothing)
   return block_max(mx, W.red);
 }
 
@@ -562,17 +578,18 @@ static __device__ __forceinline__ void solve_normal(const Matrix& A, Work& W, co
   back_solve_fast(m, W);
   phase_end(W, 3, t0);
   if (!refine) return;                                // (nobody would look at the residual)
+  const bool pymode = p.refine_mode != 0;             // _ldl.pyx:144-148: signed test, dy -= correction
   t0 = phase_begin(W);
-  double maxr = residual_M(m, W);
+  double maxr = residual_M(m, W, pymode);
   phase_end(W, 4, t0);
   int nref = 0;
   while (maxr > p.refine_tol && nref < p.max_refine) {
     t0 = phase_begin(W);
     fwd_solve_fast(m, W);
-    back_solve_fast(m, W);
+    back_solve_fast(m, W, pymode ? -1.0 : 1.0);
     phase_end(W, 3, t0);
     t0 = phase_begin(W);
-    maxr = residual_M(m, W);
+    maxr = residual_M(m, W, pymode);
     phase_end(W, 4, t0);
     nref++;
   }
@@ -613,23 +630,25 @@ static __device__ __forceinline__ void prepare_rhs(const Matrix& A, Work& W, dou
 // dx, dz, ratio test, update (primal_normal.cl:122-156) using the stored t.  Leaves
 // v = A'y of the UPDATED y in W.t: v_new = (c - t + mu/x) + theta A'dy.
 template <bool VS>
-static __device__ __forceinline__ void step(const Matrix& A, Work& W, double mu, double r) {
+static __device__ __forceinline__ void step(const Matrix& A, Work& W, double mu, const Params& p) {
+  const double r = p.r;
+  const bool dz1 = p.dz_mode != 0;
   const int m = A.m, n = A.n, tid = threadIdx.x;
   const double c_first = (tid < n) ? W.c[tid] : 0.0;
   At_times(A, W.dy, W.w);
-  double th = 0.0;
+  double th = p.theta_floor ? 0.0 : -INFINITY;   // primal_normal.cl:134 / normal_eqns.py:92
   for (int j = tid; j < n; j += NT) {
     double xj = W.x[j], zj = W.z[j];
     double dx = (W.t[j] - W.w[j]) * xj / zj;
-    double dz = (mu - zj * dx) / xj - zj;
+    double dz = dz1 ? (mu - xj * zj - zj * dx) / xj : (mu - zj * dx) / xj - zj;
     th = fmax(th, fmax(-dz / zj, -dx / xj));
     W.d[j] = dx;                                 // (d = x/z is dead by now; t and w are still needed)
   }
-  th = block_max(th, W.red);
+  th = p.theta_floor ? block_max(th, W.red) : -block_max_signed(-th, W.red);
   const double theta = fmin(r / th, 1.0);
   for (int j = tid; j < n; j += NT) {
     const double xj = W.x[j], zj = W.z[j], dx = W.d[j];
-    const double dz = (mu - zj * dx) / xj - zj;  // same expression, same operands as above
+    const double dz = dz1 ? (mu - xj * zj - zj * dx) / xj : (mu - zj * dx) / xj - zj;   // same expression, same operands as above
     const double cj = (j == tid) ? c_first : W.c[j];
     W.t[j] = (cj - W.t[j] + mu / xj) + theta * W.w[j];
     W.z[j] = zj + theta * dz;

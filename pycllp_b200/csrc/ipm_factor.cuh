@@ -1394,7 +1394,7 @@ static __device__ __forceinline__ bool factor_ldl_ahead(int m, Work& W, double b
 // S <- L^-T S ; dy += S     (second half of ldl.cl:529-536), blocks of 32 columns:
 // the part of each dot product below the block is a warp-per-column reduction on all
 // warps, the 32x32 triangle is back-substituted by warp 0 in registers with shuffles.
-static __device__ __forceinline__ void back_solve_fast(int m, Work& W) {
+static __device__ __forceinline__ void back_solve_fast(int m, Work& W, double sign = 1.0) {
   const int tid = threadIdx.x, lane = tid & 31, warp = warp_id();
   const double* __restrict__ L = W.L;
   double* __restrict__ S = W.S;
@@ -1428,7 +1428,7 @@ static __device__ __forceinline__ void back_solve_fast(int m, Work& W) {
       }
       if (valid) {
         S[j] = w;
-        W.dy[j] += w;
+        W.dy[j] += sign * w;
       }
     }
     __syncthreads();

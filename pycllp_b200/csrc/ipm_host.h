@@ -15,5 +15,6 @@ cudaError_t launch_solve(const Matrix& A, const Batch& B, const Scratch& sc, con
 cudaError_t launch_ldl_hook(int N, int m, const double* AA, double* L, double* D, int modified,
                             double beta, double delta, double* scratch, size_t slot, int grid,
                             cudaStream_t stream);
+cudaError_t launch_fp64_probe(double* out, int blocks, int iters, cudaStream_t stream);
 int solve_kernel_max_blocks_per_sm(size_t smem_bytes, int L_in_smem, int vec_in_smem);
 }  // namespace pb200

@@ -53,13 +53,21 @@ template <bool LS, bool VS>
 static __device__ __forceinline__ void ipm_solve_one(const Matrix& A, const Batch& B, Work& W, const Params& p, int q) {
   const int m = A.m, n = A.n, tid = threadIdx.x;
   W.c = B.c + (size_t)q * n;
+  const bool given = B.hook || B.warm;            // start from the caller's x, z, y (primal_normal.cl:213-219)
+  const size_t ld0n = B.ld_0 ? B.ld_0 : (size_t)n, ld0m = B.ld_0 ? B.ld_0 : (size_t)m;
   for (int j = tid; j < n; j += NT) {
-    W.x[j] = B.hook ? B.x0[(size_t)q * n + j] : 1.0;   // initialize_xzyw, primal_normal.cl:14-28
-    W.z[j] = B.hook ? B.z0[(size_t)q * n + j] : 1.0;
+    double x0 = 1.0, z0 = 1.0;                       // initialize_xzyw, primal_normal.cl:14-28
+    if (given) {
+      x0 = B.x0[(size_t)q * ld0n + j];
+      z0 = B.z0[(size_t)q * ld0n + j];
+      if (B.warm) { x0 = fmax(x0, p.warm_floor); z0 = fmax(z0, p.warm_floor); }
+    }
+    W.x[j] = x0;
+    W.z[j] = z0;
   }
   for (int i = tid; i < m; i += NT) {
     W.b[i] = B.b[(size_t)q * m + i];
-    W.y[i] = B.hook ? B.y0[(size_t)q * m + i] : 1.0;
+    W.y[i] = given ? B.y0[(size_t)q * ld0m + i] : 1.0;
   }
   __syncthreads();
 
@@ -75,20 +83,29 @@ static __device__ __forceinline__ void ipm_solve_one(const Matrix& A, const Batc
   int stat = 5;                                   // primal_normal.cl:225
   double normr0 = INFINITY, norms0 = INFINITY;    // HUGE_VALF/10, :227-228
   int iter;
-  // v = A'y is carried over from the previous step (one pass over A less) for the first 64
-  // iterations -- every LP that converges is done long before -- and recomputed from y like the
-  // reference does afterwards, which bounds the drift on the long diverging runs of infeasible LPs
+  // v = A'y is carried over from the previous step (one pass over A less) for the first
+  // p.carry_v iterations (default 64: every LP that converges is done long before) and recomputed
+  // from y like the reference does afterwards, which bounds the drift on the long diverging runs
+  // of infeasible LPs; carry_v = 0 recomputes it every iteration (primal_normal.cl:76-94)
   bool carry_v = false;
   for (iter = 0; iter < p.max_iter; iter++) {
     double g = 0.0;
     for (int j = tid; j < n; j += NT) g += W.z[j] * W.x[j];
     const double gamma = block_sum(g, W.red);
-    const double mu = p.delta * gamma / (double)(n + m);          // :272
+    const double mu = p.delta * gamma / (double)(p.mu_mode ? n : n + m);   // :272 (normal_eqns.py:65)
     double normr, norms;
     long long t0 = phase_begin(W);
     prepare_rhs<VS>(A, W, mu, normr, norms, carry_v);
-    carry_v = iter + 1 < 64;
+    // (only while the primal residual still shrinks by >= 10 % per step: on an infeasible LP it
+    // stalls, y diverges and the rounding noise of A'y -- which the reference recomputes every
+    // iteration -- is what eventually trips the |sigma| > 10 |sigma_0| test, primal_normal.cl:266;
+    // a carried v has a different noise and misses it: tests/test_gpu_features.py)
+    carry_v = iter + 1 < p.carry_v && normr <= 0.9 * normr0;
     phase_end(W, 0, t0);
+    if (B.trace && tid == 0 && iter < B.trace_iters) {           // :250-252 (the kernel's verbose > 1 printf)
+      double* tr = B.trace + ((size_t)q * B.trace_iters + iter) * 3;
+      tr[0] = normr; tr[1] = norms; tr[2] = gamma;
+    }
     if (normr < p.eps && norms < p.eps && gamma < p.eps) { stat = 0; break; }   // :256-259
     if (normr > 10 * normr0 && normr > p.eps) { stat = 2; break; }              // :261-264
     if (norms > 10 * norms0 && norms > p.eps) { stat = 4; break; }              // :266-269
@@ -96,18 +113,26 @@ static __device__ __forceinline__ void ipm_solve_one(const Matrix& A, const Batc
     // and factor loops need every register they can get (block-uniform values, benign race)
     W.red[RED_KEEP] = normr; W.red[RED_KEEP + 1] = norms; W.red[RED_KEEP + 2] = mu;
     solve_normal<LS, VS>(A, W, p);
+    if (p.nan_guard) {                                            // normal_eqns.py:85-87
+      int bad = 0;
+      for (int i = tid; i < m; i += NT) bad |= isnan(W.dy[i]);
+      if (__syncthreads_or(bad)) { stat = 3; break; }
+    }
     t0 = phase_begin(W);
-    step<VS>(A, W, W.red[RED_KEEP + 2], p.r);
+    step<VS>(A, W, W.red[RED_KEEP + 2], p);
     phase_end(W, 5, t0);
     normr0 = W.red[RED_KEEP];
     norms0 = W.red[RED_KEEP + 1];
   }
-  if (B.x) for (int j = tid; j < n; j += NT) B.x[(size_t)q * n + j] = W.x[j];
-  if (B.z) for (int j = tid; j < n; j += NT) B.z[(size_t)q * n + j] = W.z[j];
-  if (B.y) for (int i = tid; i < m; i += NT) B.y[(size_t)q * m + i] = W.y[i];
+  // (warm start: x0/z0/y0 may alias the outputs -- with the same leading dimensions)
+  const size_t ldx = B.ld_x ? B.ld_x : (size_t)n, ldy = B.ld_y ? B.ld_y : (size_t)m, ldz = B.ld_z ? B.ld_z : (size_t)n;
+  const int lds = B.ld_s ? B.ld_s : 1;
+  if (B.x) for (int j = tid; j < n; j += NT) B.x[(size_t)q * ldx + j] = W.x[j];
+  if (B.z) for (int j = tid; j < n; j += NT) B.z[(size_t)q * ldz + j] = W.z[j];
+  if (B.y) for (int i = tid; i < m; i += NT) B.y[(size_t)q * ldy + i] = W.y[i];
   if (tid == 0) {
-    if (B.status) B.status[q] = stat;
-    if (B.iters) B.iters[q] = iter;
+    if (B.status) B.status[(size_t)q * lds] = stat;
+    if (B.iters) B.iters[(size_t)q * lds] = iter;
   }
   __syncthreads();
 }
@@ -174,9 +199,32 @@ ldl_hook_kernel(int N, int m, const double* AA, double* Lout, double* Dout, int 
   }
 }
 
+// FP64 tensor-core (DMMA m8n8k4) issue-rate probe: eight independent accumulator tiles per warp,
+// nothing but DMMAs in the loop.  The roofline denominator of bench.py is measured with this
+// on the box the bench runs on (MEASURED_PEAKS.json holds only HBM and bf16).
+__global__ void __launch_bounds__(NT, 1) fp64_probe_kernel(double* out, int iters) {
+  double c[8][2];
+#pragma unroll
+  for (int i = 0; i < 8; i++) c[i][0] = c[i][1] = 0.0;
+  const double a = threadIdx.x * 1e-3, b = 1.0 + threadIdx.x * 1e-6;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) dmma884(c[i][0], c[i][1], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) s += c[i][0] + c[i][1];
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 // ---------------------------------------------------------------------------------------
 // host-side launch helpers (called from cabi.cu)
 // ---------------------------------------------------------------------------------------
+cudaError_t launch_fp64_probe(double* out, int blocks, int iters, cudaStream_t stream) {
+  fp64_probe_kernel<<<blocks, NT, 0, stream>>>(out, iters);
+  return cudaGetLastError();
+}
+
 size_t smem_doubles(const Matrix& A, int L_in_smem, int vec_in_smem) {
   auto al = [](size_t v) { return (v + 15) & ~(size_t)15; };
   size_t o = RED_SIZE;

@@ -20,6 +20,14 @@ constexpr int FB_DOUBLES = 2 * 32 * 68 + 16 * 8 * 64 + 64 * 68 + 64 + 32;   // s
 struct Params {
   double eps, delta, r, ldl_delta, refine_tol;
   int max_iter, max_refine;
+  // (see pycllp_b200_params in include/pycllp_b200.h)
+  int nan_guard;     // NaN in dy => status 3 (normal_eqns.py:85-87)
+  int carry_v;       // iterations during which v = A'y is carried over instead of recomputed (0: never)
+  int mu_mode;       // 0: mu = delta gamma / (n+m) (primal_normal.cl:272) ; 1: / n (normal_eqns.py:65)
+  int refine_mode;   // 0: while max|r| > tol: dy += solve(r) (ldl.cl:645-652) ; 1: while max r > tol: dy -= solve(r) (_ldl.pyx:144-148)
+  int theta_floor;   // 1: theta = max(0, ...) (primal_normal.cl:134) ; 0: no floor (normal_eqns.py:92)
+  int dz_mode;       // 0: dz = (mu - z dx)/x - z (primal_normal.cl:143) ; 1: (mu - x z - z dx)/x (normal_eqns.py:90)
+  double warm_floor; // warm start: x0, z0 <- max(., warm_floor) (0: the raw previous point, primal_normal.cl:213-219)
 };
 
 // The shared constraint matrix and everything precomputed from it at setup.
@@ -97,6 +105,16 @@ struct Batch {
   const double *b, *c;     // (N, m), (N, n)
   double *x, *y, *z;       // (N, n), (N, m), (N, n)   (may be null)
   int *status, *iters;     // (N)                      (may be null)
+  // leading dimensions of the outputs (0 = contiguous: n, m, n doubles; 1, 1 ints): a packed
+  // per-problem record [x | y | z | status, iters] is written in place for the multi-GPU gather
+  size_t ld_x, ld_y, ld_z;
+  int ld_s;
+  size_t ld_0;             // leading dimension of x0, z0, y0 (0 = contiguous)
+  // warm start: begin from x0, z0 (N,n), y0 (N,m) instead of x = z = y = 1 (they may alias x, z, y)
+  int warm;
+  // optional (N, trace_iters, 3): |rho|, |sigma|, gamma of every iteration (primal_normal.cl:250-252)
+  double* trace;
+  int trace_iters;
   // hook mode (one normal-equations solve on given state): x0,z0 (N,n), y0 (N,m) in, dy out
   int hook;
   const double *x0, *z0, *y0;

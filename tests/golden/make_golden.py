@@ -103,3 +103,12 @@ L1, D1 = ref.ldl(AA, modified=False)
 beta = float(np.sqrt(np.amax(AA)))
 L2, D2 = ref.ldl(AA, modified=True, beta=beta, delta=1e-6)
 save("kernel_ldl", AA=AA, L_plain=L1, D_plain=D1, beta=beta, L_mod=L2, D_mod=D2)
+
+# Oracle A (the reference's CPU solver, normal_eqns.py + _ldl.pyx): first 4 LPs of config 1.
+# Its statuses are rounding-noise driven: stored for the objective cross-check of
+# the 'py' preset only.
+from oracle import oracle_a  # noqa: E402
+if oracle_a.available():
+    A, b, c = random_equality_arrays(50, 50, 0.1, 64)
+    r = oracle_a.solve(A, b[:4], c[:4])
+    save("cfg1_oracle_a", A=A, b=b[:4], c=c[:4], **r)

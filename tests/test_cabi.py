@@ -31,9 +31,17 @@ def test_header_symbols_are_exported():
 
 def test_params_struct_layout_matches_header():
     from pycllp_b200._cabi import Params
-    assert [f[0] for f in Params._fields_] == ["eps", "delta", "r", "ldl_delta", "refine_tol",
-                                               "max_iter", "max_refine"]
-    assert ctypes.sizeof(Params) == 5 * 8 + 2 * 4
+    # the field order of pycllp_b200_params in the header, parsed from the header itself
+    text = open(os.path.join(ROOT, "include", "pycllp_b200.h")).read()
+    body = re.search(r"typedef struct \{(.*?)\} pycllp_b200_params;", text, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    decl = re.findall(r"\b(double|int)\s+([a-z_, ]+);", body)
+    names = [n.strip() for _, group in decl for n in group.split(",")]
+    kinds = [t for t, group in decl for _ in group.split(",")]
+    assert [f[0] for f in Params._fields_] == names
+    assert [f[1] for f in Params._fields_] == [ctypes.c_double if k == "double" else ctypes.c_int for k in kinds]
+    assert names[:7] == ["eps", "delta", "r", "ldl_delta", "refine_tol", "max_iter", "max_refine"]
+    assert ctypes.sizeof(Params) == 5 * 8 + 8 * 4 + 8
 
 
 def test_no_cpu_fallback():

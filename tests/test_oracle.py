@@ -144,3 +144,26 @@ def test_infeasible_and_limits(oracle):
     p.max_iter = 3
     r = oracle.solve_dense(g["A"], g["b"][:2], g["c"][:2], params=p)
     assert (r.status == 5).all() and (r.iters == 3).all()
+
+
+def test_oracle_a_reference_cpu_solver():
+    """Oracle A = the reference's DensePrimalNormalSolver (normal_eqns.py restated in
+    oracle/oracle_a.py + pycllp/_ldl.pyx compiled as is into oracle/_ref): known answers of
+    tests/test_vanderbei.py:25-42 and the committed config-1 fixture."""
+    from oracle import oracle_a
+    if not oracle_a.available():
+        pytest.skip("oracle/_ref/_ldl*.so not built (needs /root/reference and cython)")
+    for fn in (problems.vanderbei_2_9, problems.vanderbei_2_10):
+        lp, xopt = fn()
+        A, b, c = problems.equality_arrays(lp)
+        r = oracle_a.solve(A, b, c)
+        assert r["status"][0] == 0
+        np.testing.assert_allclose(r["x"][0, :len(xopt)], xopt, rtol=1e-6, atol=1e-6)
+    g = golden("cfg1_oracle_a")
+    r = oracle_a.solve(g["A"], g["b"][:1], g["c"][:1])
+    np.testing.assert_allclose(r["x"][0] @ g["c"][0], g["x"][0] @ g["c"][0], rtol=1e-9)
+    # same optimum as the OpenCL-kernel semantics (the parity target), to the accuracy its noisy
+    # termination allows
+    gc = golden("cfg1_dense")
+    np.testing.assert_allclose(np.einsum("ij,ij->i", g["x"], g["c"]),
+                               np.einsum("ij,ij->i", gc["x"][:4], gc["c"][:4]), rtol=1e-6)
