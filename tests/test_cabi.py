@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _declared_symbols():
     text = open(os.path.join(ROOT, "include", "pycllp_b200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(pycllp_b200_[a-z_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(pycllp_b200_[a-z0-9_]+)\s*\(", text)))
 
 
 def test_header_symbols_are_exported():
