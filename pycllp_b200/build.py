@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpycllp_b200.so")
-SOURCES = ["ipm_kernels.cu", "cabi.cu"]
+SOURCES = ["ipm_kernels.cu", "ipm_kernels_py.cu", "cabi.cu"]
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
 NVCC_FLAGS = [
@@ -19,6 +19,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC", "-shared",
     "-Xptxas", "-v",
     "-cudart", "shared",
+    "--threads", "3",          # the translation units compile side by side
 ]
 
 

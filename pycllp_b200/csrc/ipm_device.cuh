@@ -69,6 +69,22 @@ __device__ __forceinline__ double block_max(double v, double* red) {
   return __shfl_sync(0xffffffffu, r, 0);     // provably warp-uniform
 }
 
+// two maxima of non-negative values with one exchange through shared memory (red: >= 64 doubles)
+__device__ __forceinline__ double block_max2(double v, double& w, double* red) {
+  const int lane = threadIdx.x & 31, warp = warp_id();
+  v = warp_max(v);
+  w = warp_max(w);
+  if (lane == 0) { red[warp] = v; red[NWARP + warp] = w; }
+  __syncthreads();
+  double r = (lane < NWARP) ? red[lane] : 0.0;
+  double q = (lane < NWARP) ? red[NWARP + lane] : 0.0;
+  r = warp_max(r);
+  q = warp_max(q);
+  __syncthreads();
+  w = __shfl_sync(0xffffffffu, q, 0);
+  return __shfl_sync(0xffffffffu, r, 0);
+}
+
 // minimum over the block of values of any sign (used as max = -min(-v))
 __device__ __forceinline__ double block_max_signed(double negv, double* red) {
   const int lane = threadIdx.x & 31, warp = warp_id();
@@ -514,7 +530,9 @@ static __device__ __forceinline__ double residual_M(int m, Work& W, bool signed_
 }
 
 // factor + solve + refinement (ldl.cl:602-653); requires W.d, W.RHS set. Leaves dy.
-template <bool LS, bool VS>
+// CL: the constants of the reference's OpenCL path (preset "cl") are compile-time here -- the
+// branches of the "py" conventions cost the common path registers and issue slots otherwise.
+template <bool LS, bool VS, bool CL>
 static __device__ __forceinline__ void solve_normal(const Matrix& A, Work& W, const Params& p) {
   const int m = A.m, tid = threadIdx.x;
   long long t0 = phase_begin(W);
@@ -556,7 +574,7 @@ static __device__ __forceinline__ void solve_normal(const Matrix& A, Work& W, co
   phase_end(W, 6, t0);
   bool redo = true;
   const bool ahead = LS && m <= 208;                  // (L in shared memory: m <= ~202 in practice)
-  if (ahead) redo = factor_ldl_ahead(m, W, beta, p.ldl_delta, W.RHS, W.S);
+  if (ahead) redo = factor_ldl_ahead_call(m, W.L, W.D, W.P, W.red, W.prof, beta, p.ldl_delta, W.RHS, W.S);
   const bool big = !LS && m > SB;                     // factor in global memory: super-panel sweep
   if (big) redo = factor_ldl_big(m, W, beta, p.ldl_delta, W.RHS, W.S);
   if (redo) {
@@ -578,7 +596,7 @@ static __device__ __forceinline__ void solve_normal(const Matrix& A, Work& W, co
   back_solve_fast(m, W);
   phase_end(W, 3, t0);
   if (!refine) return;                                // (nobody would look at the residual)
-  const bool pymode = p.refine_mode != 0;             // _ldl.pyx:144-148: signed test, dy -= correction
+  const bool pymode = !CL && p.refine_mode != 0;      // _ldl.pyx:144-148: signed test, dy -= correction
   t0 = phase_begin(W);
   double maxr = residual_M(m, W, pymode);
   phase_end(W, 4, t0);
@@ -629,22 +647,30 @@ static __device__ __forceinline__ void prepare_rhs(const Matrix& A, Work& W, dou
 
 // dx, dz, ratio test, update (primal_normal.cl:122-156) using the stored t.  Leaves
 // v = A'y of the UPDATED y in W.t: v_new = (c - t + mu/x) + theta A'dy.
-template <bool VS>
+template <bool VS, bool CL>
 static __device__ __forceinline__ void step(const Matrix& A, Work& W, double mu, const Params& p) {
   const double r = p.r;
-  const bool dz1 = p.dz_mode != 0;
+  const bool dz1 = !CL && p.dz_mode != 0;
+  const bool floor0 = CL || p.theta_floor != 0;
   const int m = A.m, n = A.n, tid = threadIdx.x;
   const double c_first = (tid < n) ? W.c[tid] : 0.0;
   At_times(A, W.dy, W.w);
-  double th = p.theta_floor ? 0.0 : -INFINITY;   // primal_normal.cl:134 / normal_eqns.py:92
+  double th = floor0 ? 0.0 : -INFINITY;          // primal_normal.cl:134 / normal_eqns.py:92
+  double big = 0.0;                              // max_j mu / x_j: the cancellation in the carried v
   for (int j = tid; j < n; j += NT) {
     double xj = W.x[j], zj = W.z[j];
     double dx = (W.t[j] - W.w[j]) * xj / zj;
     double dz = dz1 ? (mu - xj * zj - zj * dx) / xj : (mu - zj * dx) / xj - zj;
     th = fmax(th, fmax(-dz / zj, -dx / xj));
+    big = fmax(big, mu / xj);
     W.d[j] = dx;                                 // (d = x/z is dead by now; t and w are still needed)
   }
-  th = p.theta_floor ? block_max(th, W.red) : -block_max_signed(-th, W.red);
+  // v_new = (c - t + mu/x) + theta A'dy below recovers v = A'y from t = c - v + mu/x with an error
+  // of eps max_j(mu/x_j); on the central path mu/x_j ~ z_j and that is rounding level, far from
+  // it (infeasible LPs) it is not: the caller stops carrying v then
+  if (floor0) th = block_max2(th, big, W.red);
+  else { th = -block_max_signed(-th, W.red); big = block_max(big, W.red); }
+  if (tid == 0) W.red[RED_KEEP + 3] = big;
   const double theta = fmin(r / th, 1.0);
   for (int j = tid; j < n; j += NT) {
     const double xj = W.x[j], zj = W.z[j], dx = W.d[j];

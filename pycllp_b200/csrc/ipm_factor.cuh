@@ -586,8 +586,9 @@ __device__ __forceinline__ void su_t_store(SuCtx& c, int buf, SuT& t) {
   *reinterpret_cast<double2*>(dst + 2) = t.t1;
 }
 
-static __device__ __forceinline__ bool factor_ldl_ahead(int m, Work& W, double beta, double delta,
-                                                        const double* rhs, double* __restrict__ Sf);
+static __device__ __noinline__ bool factor_ldl_ahead_call(int m, double* L, double* D, double* P, double* red,
+                                                          unsigned long long* prof, double beta, double delta,
+                                                          const double* rhs, double* Sf);
 
 // Row solve of a 16-row x 64-column unit against the factorised 64x64 diagonal block, in
 // registers, in the accumulator layout of the DMMAs (cx: rows ra+2g, cy: rows ra+2g+1; tile t
@@ -980,7 +981,7 @@ static __device__ __noinline__ bool super_panel(int m, int J0, int nbw, Work& W,
     Wb.prof = nullptr;
     // the look-ahead factorisation (serial chain on its own warp); speculative like this sweep:
     // a failure is reported to the caller, who redoes the whole factorisation
-    bad = factor_ldl_ahead(nbw, Wb, beta, delta, Sf + J0, Sf + J0);
+    bad = factor_ldl_ahead_call(nbw, Wb.L, Wb.D, Wb.P, Wb.red, nullptr, beta, delta, Sf + J0, Sf + J0);
   }
   // block -> L ; tables of the row solve
   for (int e = tid; e < nbw * nbw; e += NT) {
@@ -1389,6 +1390,17 @@ static __device__ __forceinline__ bool factor_ldl_ahead(int m, Work& W, double b
     }
   }
   return __syncthreads_or(bad) != 0;
+}
+
+// Out-of-line entry (like the SYRK): inlined into the persistent kernel the chain warp's code is
+// at the mercy of the register allocation of everything around it (measured: +25 % on the 8x8
+// pivot blocks after unrelated code was added to the kernel); as a real function it gets its own.
+static __device__ __noinline__ bool factor_ldl_ahead_call(int m, double* L, double* D, double* P, double* red,
+                                                          unsigned long long* prof, double beta, double delta,
+                                                          const double* rhs, double* Sf) {
+  Work W;
+  W.L = L; W.D = D; W.P = P; W.red = red; W.prof = prof;
+  return factor_ldl_ahead(m, W, beta, delta, rhs, Sf);
 }
 
 // S <- L^-T S ; dy += S     (second half of ldl.cl:529-536), blocks of 32 columns:

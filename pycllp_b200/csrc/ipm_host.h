@@ -12,6 +12,8 @@ size_t vec_area_doubles(const Matrix& A);
 size_t smem_doubles(const Matrix& A, int L_in_smem, int vec_in_smem);
 cudaError_t launch_solve(const Matrix& A, const Batch& B, const Scratch& sc, const Params& p,
                          int grid, size_t smem_bytes, cudaStream_t stream);
+cudaError_t launch_solve_py(const Matrix& A, const Batch& B, const Scratch& sc, const Params& p,
+                            int grid, size_t smem_bytes, cudaStream_t stream);
 cudaError_t launch_ldl_hook(int N, int m, const double* AA, double* L, double* D, int modified,
                             double beta, double delta, double* scratch, size_t slot, int grid,
                             cudaStream_t stream);
