@@ -98,6 +98,30 @@ int pycllp_b200_setup_dense(pycllp_b200_engine *e, int m, int n, const double *A
 int pycllp_b200_setup_sparse(pycllp_b200_engine *e, int m, int n, const int *indptr,
                              const int *indices, const double *data, int max_problems);
 
+/* Numeric factor of the SPARSE path (takes effect at the next setup_sparse):
+ *   1  tiles: L is stored and computed on the symbolic fill pattern only, at 8x8-tile granularity
+ *      (block elimination tree + block fill analysed once per engine; memory ~ nnz(L); DMMA tile
+ *      updates) -- the counterpart of sparse_factor_primal_normal on the Lindptr/Lindices pattern
+ *      (ldl.cl:381-502, cl.py:185-196, prototype sparse_ldl.py:72-152);
+ *   2  dense: the packed dense kernels (exact too: entries outside the fill stay zero);
+ *   0  auto (default): tiles when m > 512 and the block fill is below 40 % of the triangle.
+ * The tiles mode keeps no copy of M and therefore has no iterative refinement (max_refine must
+ * be 0, which is the sparse default and what the reference's sparse path does, ldl.cl:698-711). */
+int pycllp_b200_set_sparse_factor(pycllp_b200_engine *e, int mode);
+/* After setup_sparse: which factor is in use, its doubles per LP vs the dense m(m+1)/2, the tile
+ * pair updates per factorisation and the block fill fraction. Any pointer may be NULL. */
+int pycllp_b200_sparse_info(const pycllp_b200_engine *e, int *tiles_mode, long long *factor_doubles,
+                            long long *dense_factor_doubles, long long *update_pairs,
+                            double *tile_fill);
+
+/* Host-only (no device needed): the symbolic analysis behind mode 1 for the CSR pattern of A.
+ * Block column J of L owns tiles colptr[J] .. colptr[J+1]-1 (diagonal tile first; row[t], col[t] =
+ * block row / column of tile t); tile t receives - L(upda[p]) D L(updb[p])' for
+ * p in [updptr[t], updptr[t+1]).  Call with NULL arrays to get nbk, ntiles and pairs first. */
+int pycllp_b200_tile_analysis(int m, int n, const int *indptr, const int *indices, int *nbk,
+                              int *ntiles, long long *pairs, int *colptr, int *row, int *col,
+                              int *updptr, int *upda, int *updb);
+
 int pycllp_b200_set_params(pycllp_b200_engine *e, const pycllp_b200_params *p);
 int pycllp_b200_get_params(const pycllp_b200_engine *e, pycllp_b200_params *p);
 /* All constants of one of the reference's implementations at once: "cl" (the OpenCL

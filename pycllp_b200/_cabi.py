@@ -83,6 +83,12 @@ def load_library():
     lib.pycllp_b200_info.argtypes = [_vp, _ip, _ip, _ip, ctypes.POINTER(ctypes.c_size_t),
                                      ctypes.POINTER(ctypes.c_size_t), _ip]
     lib.pycllp_b200_phase_profile.argtypes = [_vp, ctypes.c_int, ctypes.POINTER(ctypes.c_ulonglong)]
+    lib.pycllp_b200_tile_analysis.argtypes = [ctypes.c_int, ctypes.c_int, _ip, _ip, _ip, _ip,
+                                              ctypes.POINTER(ctypes.c_longlong)] + [_ip] * 6
+    lib.pycllp_b200_set_sparse_factor.argtypes = [_vp, ctypes.c_int]
+    lib.pycllp_b200_sparse_info.argtypes = [_vp, _ip, ctypes.POINTER(ctypes.c_longlong),
+                                            ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_longlong),
+                                            _dp]
     _lib = lib
     return lib
 
@@ -97,6 +103,35 @@ def _i(a):
 
 def _f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def tile_analysis(csr):
+    """Host-only symbolic analysis of the tile-sparse factor for the pattern of ``csr`` (what
+    ``setup_sparse`` computes for ``factor='tiles'``); returns the tile structure as numpy arrays."""
+    lib = load_library()
+    csr = csr.tocsr()
+    csr.sort_indices()
+    m, n = csr.shape
+    indptr = np.ascontiguousarray(csr.indptr, dtype=np.int32)
+    indices = np.ascontiguousarray(csr.indices, dtype=np.int32)
+    nbk, nt, pairs = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_longlong(0)
+    null = ctypes.POINTER(ctypes.c_int)()
+    rc = lib.pycllp_b200_tile_analysis(m, n, _i(indptr), _i(indices), ctypes.byref(nbk), ctypes.byref(nt),
+                                       ctypes.byref(pairs), null, null, null, null, null, null)
+    if rc != 0:
+        raise RuntimeError("pycllp_b200_tile_analysis failed (%d)" % rc)
+    out = dict(nbk=nbk.value, ntiles=nt.value, pairs=pairs.value,
+               colptr=np.zeros(nbk.value + 1, np.int32), row=np.zeros(nt.value, np.int32),
+               col=np.zeros(nt.value, np.int32), updptr=np.zeros(nt.value + 1, np.int32),
+               upda=np.zeros(max(pairs.value, 1), np.int32), updb=np.zeros(max(pairs.value, 1), np.int32))
+    rc = lib.pycllp_b200_tile_analysis(m, n, _i(indptr), _i(indices), ctypes.byref(nbk), ctypes.byref(nt),
+                                       ctypes.byref(pairs), _i(out["colptr"]), _i(out["row"]), _i(out["col"]),
+                                       _i(out["updptr"]), _i(out["upda"]), _i(out["updb"]))
+    if rc != 0:
+        raise RuntimeError("pycllp_b200_tile_analysis failed (%d)" % rc)
+    out["upda"] = out["upda"][:pairs.value]
+    out["updb"] = out["updb"][:pairs.value]
+    return out
 
 
 class Engine(object):
@@ -180,8 +215,14 @@ class Engine(object):
                     "pycllp_b200_setup_dense")
         self.m, self.n, self.max_problems, self.sparse = m, n, int(max_problems), False
 
-    def setup_sparse(self, csr, max_problems):
-        """``csr``: scipy.sparse CSR matrix (sorted indices)."""
+    SPARSE_FACTOR = {"auto": 0, "tiles": 1, "dense": 2}
+
+    def setup_sparse(self, csr, max_problems, factor="auto"):
+        """``csr``: scipy.sparse CSR matrix (sorted indices).  ``factor``: numeric factor of the
+        sparse path -- 'tiles' (L on its symbolic fill pattern, 8x8 tiles, memory ~ nnz(L)),
+        'dense' (packed dense kernels) or 'auto'."""
+        self._check(self._lib.pycllp_b200_set_sparse_factor(self._h, self.SPARSE_FACTOR[factor]),
+                    "pycllp_b200_set_sparse_factor")
         csr = csr.tocsr()
         csr.sort_indices()
         m, n = csr.shape
@@ -192,6 +233,17 @@ class Engine(object):
                                                        _d(data), int(max_problems)),
                     "pycllp_b200_setup_sparse")
         self.m, self.n, self.max_problems, self.sparse = m, n, int(max_problems), True
+
+    def sparse_info(self):
+        """Which numeric factor the sparse path uses and what it stores per LP."""
+        mode = ctypes.c_int(0)
+        fd, dd, up = ctypes.c_longlong(0), ctypes.c_longlong(0), ctypes.c_longlong(0)
+        fill = ctypes.c_double(0.0)
+        self._check(self._lib.pycllp_b200_sparse_info(self._h, ctypes.byref(mode), ctypes.byref(fd),
+                                                      ctypes.byref(dd), ctypes.byref(up), ctypes.byref(fill)),
+                    "pycllp_b200_sparse_info")
+        return {"factor": "tiles" if mode.value else "dense", "factor_doubles": fd.value,
+                "dense_factor_doubles": dd.value, "update_pairs": up.value, "tile_fill": fill.value}
 
     def get_params(self):
         p = Params()

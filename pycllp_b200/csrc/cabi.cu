@@ -41,6 +41,10 @@ struct pycllp_b200_engine {
   size_t dy_cap = 0;
   long long launches = 0;
   unsigned long long* d_prof = nullptr;   // phase counters (debug/profiling aid)
+  // sparse numeric factor: 0 auto, 1 tiles of the symbolic pattern (ipm_tiles.cuh), 2 dense packed
+  int sparse_factor_mode = 0;
+  long long tile_pairs = 0;               // tile-pair updates per factorisation (tiles mode)
+  double tile_fill = 0.0;                 // tiles of the block fill / tiles of the full lower triangle
 };
 
 namespace {
@@ -146,6 +150,97 @@ void free_matrix(pycllp_b200_engine* e) {
   e->ready = false;
 }
 
+
+// Symbolic analysis of the tile-sparse factor (ipm_tiles.cuh) from the lower pattern (me_i >= me_j)
+// of A A': block elimination tree and block fill at 8x8-tile granularity, natural order (the
+// reference does not reorder either, cl.py:185-196), tile ids, and for every tile (I, J) the
+// pairs (tile (I,K), tile (J,K)), K < J ascending, whose product it receives.
+struct TileSym {
+  int nbk = 0, ntiles = 0;
+  std::vector<int> colptr, row, col, updptr, upda, updb, me_pos;
+  size_t pairs = 0;
+};
+
+// returns false if the structure exceeds max_tiles (auto mode: not worth it) or 32-bit positions
+static bool tile_symbolic(int m, const std::vector<int>& me_i, const std::vector<int>& me_j,
+                          size_t max_tiles, TileSym& ts) {
+  const int nbk = (m + 7) / 8;
+  ts.nbk = nbk;
+  std::vector<std::vector<int>> st(nbk), ch(nbk);
+  for (size_t e = 0; e < me_i.size(); e++) {
+    const int I = me_i[e] >> 3, J = me_j[e] >> 3;
+    if (I > J) st[J].push_back(I);
+  }
+  std::vector<int> mark(nbk, -1);
+  size_t total = (size_t)nbk;
+  for (int J = 0; J < nbk; J++) {
+    std::vector<int> list;
+    mark[J] = J;
+    for (int I : st[J])
+      if (mark[I] != J) { mark[I] = J; list.push_back(I); }
+    for (int K : ch[J])
+      for (int I : st[K])
+        if (I > J && mark[I] != J) { mark[I] = J; list.push_back(I); }
+    std::sort(list.begin(), list.end());
+    st[J].swap(list);
+    if (!st[J].empty()) ch[st[J][0]].push_back(J);
+    total += st[J].size();
+    if (total > max_tiles || total * 64 > (size_t)INT_MAX) return false;
+  }
+  ts.ntiles = (int)total;
+  ts.colptr.assign(nbk + 1, 0);
+  ts.row.resize(total);
+  ts.col.resize(total);
+  for (int J = 0; J < nbk; J++) {
+    int t = ts.colptr[J];
+    ts.row[t] = J; ts.col[t] = J; t++;
+    for (int I : st[J]) { ts.row[t] = I; ts.col[t] = J; t++; }
+    ts.colptr[J + 1] = t;
+  }
+  // rl[J]: block columns K < J that hold a tile (J, K), ascending, with its position in st[K]
+  std::vector<std::vector<std::pair<int, int>>> rl(nbk);
+  for (int K = 0; K < nbk; K++)
+    for (size_t q = 0; q < st[K].size(); q++) rl[st[K][q]].push_back({K, (int)q});
+  ts.updptr.assign(total + 1, 0);
+  std::vector<int> pos(nbk, -1), fillpos;
+  // two passes over the same enumeration: count, then fill (the lists can be large)
+  for (int pass = 0; pass < 2; pass++) {
+    for (int J = 0; J < nbk; J++) {
+      for (int t = ts.colptr[J]; t < ts.colptr[J + 1]; t++) pos[ts.row[t]] = t;
+      for (auto& kq : rl[J]) {
+        const int K = kq.first, q = kq.second;
+        const int b = ts.colptr[K] + 1 + q;
+        for (size_t q2 = q; q2 < st[K].size(); q2++) {
+          const int a = ts.colptr[K] + 1 + (int)q2, t = pos[st[K][q2]];
+          if (pass == 0) ts.updptr[t + 1]++;
+          else { ts.upda[fillpos[t]] = a; ts.updb[fillpos[t]] = b; fillpos[t]++; }
+        }
+      }
+    }
+    if (pass == 0) {
+      size_t acc = 0;
+      for (size_t t = 0; t < total; t++) {
+        acc += (size_t)ts.updptr[t + 1];
+        if (acc > (size_t)INT_MAX) return false;
+        ts.updptr[t + 1] = (int)acc;
+      }
+      ts.pairs = acc;
+      ts.upda.resize(acc);
+      ts.updb.resize(acc);
+      fillpos.assign(ts.updptr.begin(), ts.updptr.end() - 1);
+    }
+  }
+  // where every entry of the pattern of A A' goes
+  ts.me_pos.resize(me_i.size());
+  for (size_t e = 0; e < me_i.size(); e++) {
+    const int i = me_i[e], j = me_j[e], I = i >> 3, J = j >> 3;
+    int t = ts.colptr[J];
+    if (I != J) t += 1 + (int)(std::lower_bound(st[J].begin(), st[J].end(), I) - st[J].begin());
+    ts.me_pos[e] = t * 64 + (j & 7) * 8 + (i & 7);
+  }
+  return true;
+}
+
 size_t al16(size_t v) { return (v + 15) & ~(size_t)15; }
 
 // choose the shared-memory configuration, the grid and allocate scratch + staging
@@ -154,13 +249,15 @@ int finish_setup(pycllp_b200_engine* e, int max_problems) {
   const size_t limit = e->smem_optin - 64;     // static smem (16 B) + margin
   int Ls = 1, Vs = 1;
   e->A.big = 0;
-  if (smem_doubles(e->A, 1, 1) * 8 > limit) { Ls = 0; e->A.big = 1; }
+  if (e->A.tiles || smem_doubles(e->A, 1, 1) * 8 > limit) { Ls = 0; e->A.big = 1; }
   if (smem_doubles(e->A, Ls, 1) * 8 > limit) { Vs = 0; }
   if (smem_doubles(e->A, Ls, Vs) * 8 > limit)
     return fail(e, PYCLLP_B200_ERR_ARG, "problem too large for the shared-memory work area");
   e->smem_bytes = smem_doubles(e->A, Ls, Vs) * 8;
-  const size_t lsz = packed_doubles(m);
-  size_t slot = al16((size_t)m * m);
+  // the factor: packed dense lower triangle, or (tiles mode) the tiles of the symbolic pattern
+  // only -- no m x m matrix in that case
+  const size_t lsz = e->A.tiles ? (size_t)e->A.ntiles * 64 : packed_doubles(m);
+  size_t slot = e->A.tiles ? 0 : al16((size_t)m * m);
   e->sc.off_L = slot;
   if (!Ls) slot += al16(lsz);
   e->sc.off_vec = slot;
@@ -431,6 +528,30 @@ static int setup_sparse_impl(pycllp_b200_engine* e, int m, int n, const int* ind
   me_ptr.push_back((int)tr.size());
   M.nme = (int)me_i.size();
   int rc;
+  // numeric factor: the tiles of the symbolic pattern when L is genuinely sparse, else the dense
+  // packed kernels (which also serve every shape whose factor fits in shared memory)
+  e->tile_pairs = 0; e->tile_fill = 0.0;
+  if (e->sparse_factor_mode != 2) {
+    const int nbk = (m + 7) / 8;
+    const size_t full = (size_t)nbk * (nbk + 1) / 2;
+    TileSym ts;
+    const size_t cap = e->sparse_factor_mode == 1 ? (size_t)INT_MAX / 64 : (size_t)(0.4 * (double)full) + 1;
+    const bool fits = tile_symbolic(m, me_i, me_j, cap, ts);
+    if (!fits && e->sparse_factor_mode == 1)
+      return fail(e, PYCLLP_B200_ERR_ARG, "setup_sparse: tile structure exceeds 32-bit positions");
+    if (fits && (e->sparse_factor_mode == 1 || m > 512)) {
+      M.tiles = 1; M.nbk = ts.nbk; M.ntiles = ts.ntiles;
+      e->tile_pairs = (long long)ts.pairs;
+      e->tile_fill = (double)ts.ntiles / (double)full;
+      if ((rc = upload(e, ts.colptr, &M.tl_colptr))) return rc;
+      if ((rc = upload(e, ts.row, &M.tl_row))) return rc;
+      if ((rc = upload(e, ts.col, &M.tl_col))) return rc;
+      if ((rc = upload(e, ts.updptr, &M.tl_updptr))) return rc;
+      if ((rc = upload(e, ts.upda, &M.tl_upda))) return rc;
+      if ((rc = upload(e, ts.updb, &M.tl_updb))) return rc;
+      if ((rc = upload(e, ts.me_pos, &M.me_pos))) return rc;
+    }
+  }
   if ((rc = upload(e, Ap, &M.Ap))) return rc;
   if ((rc = upload(e, Ai, &M.Ai))) return rc;
   if ((rc = upload(e, Ax, &M.Ax))) return rc;
@@ -458,6 +579,10 @@ int pycllp_b200_set_params(pycllp_b200_engine* e, const pycllp_b200_params* p) {
   if (!e || !p) return fail(e, PYCLLP_B200_ERR_ARG, "set_params: null argument");
   if (p->max_iter < 0 || p->max_refine < 0 || !(p->r > 0))
     return fail(e, PYCLLP_B200_ERR_ARG, "set_params: invalid value");
+  if (e->ready && e->A.tiles && p->max_refine > 0)
+    return fail(e, PYCLLP_B200_ERR_ARG,
+                "set_params: the tile-sparse factor keeps no copy of M, so it has no refinement "
+                "(like the reference's sparse path, ldl.cl:698-711); use max_refine = 0");
   e->p.eps = p->eps; e->p.delta = p->delta; e->p.r = p->r; e->p.ldl_delta = p->ldl_delta;
   e->p.refine_tol = p->refine_tol; e->p.max_iter = p->max_iter; e->p.max_refine = p->max_refine;
   e->p.nan_guard = p->nan_guard != 0; e->p.carry_v = p->carry_v < 0 ? 0 : p->carry_v;
@@ -471,7 +596,10 @@ int pycllp_b200_set_preset(pycllp_b200_engine* e, const char* name) {
   if (!e || !name) return fail(e, PYCLLP_B200_ERR_ARG, "set_preset: null argument");
   if (!e->ready) return fail(e, PYCLLP_B200_ERR_STATE, "set_preset: call setup_dense/setup_sparse first");
   if (!strcmp(name, "cl")) default_params(e->p, e->A.sparse != 0);
-  else if (!strcmp(name, "py")) python_params(e->p, e->A.sparse != 0);
+  else if (!strcmp(name, "py")) {
+    if (e->A.tiles) return fail(e, PYCLLP_B200_ERR_ARG, "set_preset: 'py' needs refinement; not with the tile-sparse factor");
+    python_params(e->p, e->A.sparse != 0);
+  }
   else return fail(e, PYCLLP_B200_ERR_ARG, "set_preset: unknown preset (cl, py)");
   return 0;
 }
@@ -746,6 +874,69 @@ int pycllp_b200_info(const pycllp_b200_engine* e, int* num_sms, int* grid, int* 
   if (smem_bytes) *smem_bytes = e->smem_bytes;
   if (scratch_bytes) *scratch_bytes = e->sc.slot * sizeof(double) * (size_t)e->grid;
   if (factor_in_smem) *factor_in_smem = e->sc.L_in_smem;
+  return 0;
+}
+
+// Host-only: the symbolic analysis of the tile-sparse factor for a CSR pattern (no device, no
+// engine) -- what setup_sparse computes, exposed so that the CPU test-suite can check it.
+int pycllp_b200_tile_analysis(int m, int n, const int* indptr, const int* indices, int* nbk, int* ntiles,
+                              long long* pairs, int* colptr, int* row, int* col, int* updptr, int* upda,
+                              int* updb) {
+  if (m <= 0 || n <= 0 || !indptr || !indices) return PYCLLP_B200_ERR_ARG;
+  try {
+    if (indptr[0] != 0) return PYCLLP_B200_ERR_ARG;
+    for (int i = 0; i < m; i++)
+      if (indptr[i + 1] < indptr[i]) return PYCLLP_B200_ERR_ARG;
+    const int nnz = indptr[m];
+    std::vector<std::vector<int>> colrows(n);
+    for (int i = 0; i < m; i++)
+      for (int k = indptr[i]; k < indptr[i + 1]; k++) {
+        if (indices[k] < 0 || indices[k] >= n) return PYCLLP_B200_ERR_ARG;
+        colrows[indices[k]].push_back(i);
+      }
+    (void)nnz;
+    std::vector<std::pair<int, int>> ent;
+    for (int k = 0; k < n; k++)
+      for (size_t a = 0; a < colrows[k].size(); a++)
+        for (size_t b = 0; b <= a; b++) ent.push_back({colrows[k][a], colrows[k][b]});
+    std::sort(ent.begin(), ent.end());
+    ent.erase(std::unique(ent.begin(), ent.end()), ent.end());
+    std::vector<int> me_i(ent.size()), me_j(ent.size());
+    for (size_t e = 0; e < ent.size(); e++) { me_i[e] = ent[e].first; me_j[e] = ent[e].second; }
+    TileSym ts;
+    if (!tile_symbolic(m, me_i, me_j, (size_t)INT_MAX / 64, ts)) return PYCLLP_B200_ERR_ARG;
+    if (nbk) *nbk = ts.nbk;
+    if (ntiles) *ntiles = ts.ntiles;
+    if (pairs) *pairs = (long long)ts.pairs;
+    if (colptr) std::copy(ts.colptr.begin(), ts.colptr.end(), colptr);
+    if (row) std::copy(ts.row.begin(), ts.row.end(), row);
+    if (col) std::copy(ts.col.begin(), ts.col.end(), col);
+    if (updptr) std::copy(ts.updptr.begin(), ts.updptr.end(), updptr);
+    if (upda) std::copy(ts.upda.begin(), ts.upda.end(), upda);
+    if (updb) std::copy(ts.updb.begin(), ts.updb.end(), updb);
+    return 0;
+  } catch (...) {
+    return PYCLLP_B200_ERR_ARG;
+  }
+}
+
+int pycllp_b200_set_sparse_factor(pycllp_b200_engine* e, int mode) {
+  if (!e) return PYCLLP_B200_ERR_ARG;
+  if (mode < 0 || mode > 2) return fail(e, PYCLLP_B200_ERR_ARG, "set_sparse_factor: mode must be 0 (auto), 1 (tiles) or 2 (dense)");
+  e->sparse_factor_mode = mode;
+  return 0;
+}
+
+int pycllp_b200_sparse_info(const pycllp_b200_engine* e, int* tiles_mode, long long* factor_doubles,
+                            long long* dense_factor_doubles, long long* update_pairs, double* tile_fill) {
+  if (!e) return PYCLLP_B200_ERR_ARG;
+  if (!e->ready) return PYCLLP_B200_ERR_STATE;
+  const long long m = e->A.m;
+  if (tiles_mode) *tiles_mode = e->A.tiles;
+  if (factor_doubles) *factor_doubles = e->A.tiles ? (long long)e->A.ntiles * 64 : (long long)packed_doubles((int)m);
+  if (dense_factor_doubles) *dense_factor_doubles = m * (m + 1) / 2;
+  if (update_pairs) *update_pairs = e->tile_pairs;
+  if (tile_fill) *tile_fill = e->tile_fill;
   return 0;
 }
 

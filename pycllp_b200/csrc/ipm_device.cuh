@@ -496,6 +496,7 @@ static __device__ __forceinline__ void factor_ldl(int m, Work& W, double beta, d
 }  // namespace pb200
 #include "ipm_factor.cuh"
 #include "ipm_syrk.cuh"
+#include "ipm_tiles.cuh"
 namespace pb200 {
 
 // S = RHS - M dy ; returns max |S|   (ldl.cl:577-599); M is the block's full symmetric copy
@@ -535,6 +536,10 @@ static __device__ __forceinline__ double residual_M(int m, Work& W, bool signed_
 template <bool LS, bool VS, bool CL>
 static __device__ __forceinline__ void solve_normal(const Matrix& A, Work& W, const Params& p) {
   const int m = A.m, tid = threadIdx.x;
+  if (!LS && A.tiles) {                     // genuinely sparse factor: tiles of the symbolic pattern only
+    solve_normal_tiles(A, W, p);
+    return;
+  }
   long long t0 = phase_begin(W);
   const bool refine = p.max_refine > 0;
   if (A.sparse) form_M_sparse(A, W, refine);

@@ -1224,6 +1224,148 @@ __device__ __forceinline__ void step1_solve(double* __restrict__ L, int m, int j
   }
 }
 
+// 1/d for delta <= d < 1e30: MUFU.RCP64H seed (>= 20 bits, no conversions) + two Newton steps.
+__device__ __forceinline__ double rcp_pos64(double d) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  double e = fma(-d, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-d, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
+
+// Warp 0 of factor_ldl_ahead on a FULL panel (eight columns, j0 % 8 == 0): the serial chain with
+// every value of the 8x8 block in the registers of EVERY lane.  A lone warp is bound by its
+// instruction count and by the latency of whatever it waits for; the shuffle-based diag_block
+// spends ten SHFLs per pivot on moving entries between lanes.  Here all lanes run the same
+// scalar elimination (84 FMAs + 28 multiplications + 8 reciprocals, ~95 dependent cycles per
+// pivot), so nothing moves; lane 0 stores.  The block row (rows j1..j1+7 against the block) then
+// uses the multipliers straight from those registers, one row per group of four lanes, and feeds
+// the two DMMAs of the diagonal-tile update from registers as well.
+//   blk: Wm[64] (unscaled entries D_k l_ik), D1 at +64, rinv at +72 -- read by the other warps
+// ROW: rows j1..j1+7 all exist (m - j1 >= 8) and are solved here; otherwise the caller runs block_row.
+template <bool ROW>
+static __device__ __forceinline__ void chain_panel8(int m, int j0, int par, bool wait_e3, Work& W, double delta,
+                                                    int* th, double* __restrict__ blk, double* __restrict__ Wp) {
+  const int lane = threadIdx.x & 31;
+  double* __restrict__ L = W.L;
+  const long long tb = phase_begin(W);
+  // offsets of (row j0, column j0 + jj); coff(j+1) - coff(j) = m-1-j rounded up to even
+  int cb[8];
+  cb[0] = coff(j0, m) + j0;
+  const int ev = 1 - (m & 1);
+#pragma unroll
+  for (int jj = 1; jj < 8; jj++) cb[jj] = cb[jj - 1] + (m - j0 - jj) + ((jj - 1 + ev) & 1);
+  double e[8][8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    if (j & 1) e[j][j] = L[cb[j] + j];
+#pragma unroll
+    for (int i = j + (j & 1); i < 8; i += 2) {      // (cb even, i even: 16-byte aligned)
+      const double2 v = *reinterpret_cast<const double2*>(L + cb[j] + i);
+      e[i][j] = v.x;
+      e[i + 1][j] = v.y;
+    }
+  }
+  const int hdelta = dbl_hi(delta);
+  const bool st = lane == 0;
+  bool big = false;
+  double r[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    // D_j = max(|pivot|, delta) decided on the high words (ties, NaN and huge pivots -> exact path)
+    const int hp = dbl_hi(e[j][j]) & 0x7fffffff;
+    big |= (hp == hdelta) | (hp >= 0x46293e59);                  // 0x46293e59 ~ hi word of 1e30
+    const double Dv = (hp < hdelta) ? delta : fabs(e[j][j]);
+    r[j] = rcp_pos64(Dv);
+    int h = 0;
+    double l[8];
+#pragma unroll
+    for (int i = j + 1; i < 8; i++) {
+      h = max(h, dbl_hi(e[i][j]) & 0x7fffffff);
+      l[i] = e[i][j] * r[j];
+    }
+#pragma unroll
+    for (int i = j + 1; i < 8; i++)
+#pragma unroll
+      for (int k = j + 1; k <= i; k++) e[i][k] = fma(-l[i], e[k][j], e[i][k]);
+    // scaled column j of the unit-lower block back to L storage; D, 1/D, in-block theta
+    if (st) {
+      blk[64 + j] = Dv;
+      blk[72 + j] = r[j];
+      th[j] = h;
+      l[j] = 1.0;
+      if (j & 1) L[cb[j] + j] = 1.0;
+#pragma unroll
+      for (int i = j + (j & 1); i < 8; i += 2)
+        *reinterpret_cast<double2*>(L + cb[j] + i) = make_double2(l[i], l[i + 1]);
+    }
+  }
+  if (st) {
+    // Wm[i][k] = D_k l_ik = the unscaled entry (k < i); entries k >= i of a row are never read
+#pragma unroll
+    for (int i = 1; i < 8; i++)
+#pragma unroll
+      for (int k = 0; k < i; k += 2)
+        *reinterpret_cast<double2*>(blk + i * 8 + k) = make_double2(e[i][k], (k + 1 < i) ? e[i][k + 1] : 0.0);
+    if (big) th[0] = 0x7ff00000;
+  }
+  __syncwarp();
+  if (lane < 8) W.D[j0 + lane] = blk[64 + lane];
+  nbar_arrive(BAR_ED + par, NT);                  // block p eliminated
+  phase_end(W, 9, tb);
+  const long long tw = phase_begin(W);
+  if (wait_e3) nbar_sync(BAR_E3 + (par ^ 1), NT); // others are done with panel p-1
+  phase_end(W, 12, tw);
+  const long long tr = phase_begin(W);
+  if (ROW) {
+    const unsigned FULL = 0xffffffffu;
+    const int g = lane >> 2, tg = lane & 3;
+    double c[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) c[k] = L[cb[k] + 8 + g];
+    int hmine = 0;
+    double b1 = 0.0, b2 = 0.0;                        // B fragments of the tile update: unscaled entries k = tg, 4 + tg
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int hk = __reduce_max_sync(FULL, dbl_hi(c[k]) & 0x7fffffff);
+      if (lane == k) hmine = hk;
+      if (tg == 0) Wp[k * PBS + g] = c[k];            // unscaled: the 8-column multiplier table W'
+      if (tg == (k & 3)) {
+        if (k < 4) b1 = c[k];
+        else b2 = c[k];
+      }
+      const double lk = c[k] * r[k];
+#pragma unroll
+      for (int jj = k + 1; jj < 8; jj++) c[jj] = fma(-lk, e[jj][k], c[jj]);
+      c[k] = lk;
+    }
+    if (tg == 0) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) L[cb[k] + 8 + g] = c[k];
+    }
+    if (lane < 8) atomicMax(&th[lane], hmine);          // (the other warps add their rows concurrently)
+    // diagonal tile of panel j1 -= L(block, panel j0) Wp^T: fragments from this lane's row
+    const double a1 = (tg == 0) ? c[0] : (tg == 1) ? c[1] : (tg == 2) ? c[2] : c[3];
+    const double a2 = (tg == 0) ? c[4] : (tg == 1) ? c[5] : (tg == 2) ? c[6] : c[7];
+    double d0 = 0.0, d1 = 0.0;
+    dmma884(d0, d1, a1, b1);
+    dmma884(d0, d1, a2, b2);
+    // (row j1+g, columns j1+2tg, j1+2tg+1): cb of the next panel's columns
+    const int j1 = j0 + 8;
+    const int q0i = coff(j1 + 2 * tg, m) + j1 + g, q1i = coff(j1 + 2 * tg + 1, m) + j1 + g;
+    const double v0 = L[q0i], v1 = L[q1i];             // (both loads before the stores)
+    if (2 * tg <= g) L[q0i] = v0 - d0;
+    if (2 * tg + 1 <= g) L[q1i] = v1 - d1;
+    __syncwarp();
+  }
+  if (ROW) {
+    nbar_arrive(BAR_EB + par, NT);                  // W' of panel p published
+    phase_end(W, 8, tr);
+  }
+}
+
 static __device__ __forceinline__ bool factor_ldl_ahead(int m, Work& W, double beta, double delta,
                                                         const double* rhs, double* __restrict__ Sf) {
   const int tid = threadIdx.x, lane = tid & 31, warp = warp_id();
@@ -1254,15 +1396,23 @@ static __device__ __forceinline__ bool factor_ldl_ahead(int m, Work& W, double b
       const int j0 = 8 * p, nb = min(NB, m - j0), par = p & 1;
       int* th = thbuf + par * 8;
       double* blk = xtra + 80 * par;
-      const long long tb = phase_begin(W);
-      diag_block(m, j0, nb, W, delta, th, blk, blk + 64, blk + 72);
-      __syncwarp();
-      if (lane < nb) D[j0 + lane] = blk[64 + lane];
-      nbar_arrive(BAR_ED + par, NT);                  // block p eliminated
-      phase_end(W, 9, tb);
-      const long long tw = phase_begin(W);
-      if (p > 0) nbar_sync(BAR_E3 + (par ^ 1), NT);   // others are done with panel p-1
-      phase_end(W, 12, tw);
+      if (nb == NB && m - j0 >= 16) {                 // full panel, full block row below it
+        chain_panel8<true>(m, j0, par, p > 0, W, delta, th, blk, Wp);
+        continue;
+      }
+      if (nb == NB) {
+        chain_panel8<false>(m, j0, par, p > 0, W, delta, th, blk, Wp);
+      } else {
+        const long long tb = phase_begin(W);
+        diag_block(m, j0, nb, W, delta, th, blk, blk + 64, blk + 72);
+        __syncwarp();
+        if (lane < nb) D[j0 + lane] = blk[64 + lane];
+        nbar_arrive(BAR_ED + par, NT);                  // block p eliminated
+        phase_end(W, 9, tb);
+        const long long tw = phase_begin(W);
+        if (p > 0) nbar_sync(BAR_E3 + (par ^ 1), NT);   // others are done with panel p-1
+        phase_end(W, 12, tw);
+      }
       const long long tr = phase_begin(W);
       if (j0 + 8 < m) block_row(m, j0, nb, W, blk, blk + 72, th, Wp);
       nbar_arrive(BAR_EB + par, NT);                  // W' of panel p published

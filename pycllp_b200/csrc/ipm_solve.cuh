@@ -158,7 +158,7 @@ ipm_solve_kernel(Matrix A, Batch B, Scratch sc, Params p) {
   carve<LS, VS>(A, sc, smem, W);
   if (W.prof && threadIdx.x < 16) reinterpret_cast<unsigned long long*>(W.red + RED_PROF)[threadIdx.x] = 0;
   ring_init(W);
-  if (A.sparse && p.max_refine > 0) {   // entries outside the pattern of A A' are never written again
+  if (A.sparse && !A.tiles && p.max_refine > 0) {   // entries outside the pattern of A A' are never written again
     const size_t mm = (size_t)A.m * A.m;
     for (size_t e = threadIdx.x; e < mm; e += NT) W.M[e] = 0.0;
     __syncthreads();

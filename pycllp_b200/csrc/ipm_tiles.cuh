@@ -1,0 +1,265 @@
+// ipm_tiles.cuh -- batched SPARSE numeric LDL' on the symbolic pattern (block-sparse, 8x8 tiles).
+//
+// Replaces sparse_factor_primal_normal / sparse_forward_backward_primal_normal (ldl.cl:381-502,
+// 540-574; prototype sparse_ldl.py:72-152) for constraint matrices whose factor is genuinely
+// sparse.  The reference stores L on the pattern of the Cholesky factor of A A' in CSR-lower
+// (diagonal last) and finds every L_ij by a merge of rows i and j; here the pattern is analysed
+// once per engine at the granularity of 8x8 tiles (cabi.cu: block elimination tree, block fill,
+// the list of tile pairs that update every tile), and each LP keeps ONLY the tiles of that
+// pattern in its scratch slot -- memory ~ nnz(L), no m x m array anywhere.
+//
+// Per block column J (left-looking, natural order like the reference):
+//   A. every tile (I, J) -= sum_K L(I,K) D_K L(J,K)'  over its precomputed pair list: one warp per
+//      tile, two DMMA m8n8k4 per pair, fragments straight from the tiles (a tile column is 8
+//      consecutive doubles, a fragment load is one coalesced 256-byte request);
+//   B. the eight columns of the block are eliminated one at a time across ALL rows of the block
+//      column by the exact sequential rule of ldl.cl:349-376:
+//        theta_j = max_i |c_ij| ; D_j = max(|D_j|, (theta_j/beta)^2, delta) ; L_ij = c_ij / D_j ;
+//        c_ij' -= L_ij c_j'j   (j' = j+1 .. 7 of this block)
+//      one thread per row, the theta reduction over a named barrier that only the warps owning
+//      rows take part in.  No speculation, hence no fallback path.
+// The triangular solves walk the same tiles (one warp, column-oriented forward, dot-product
+// backward) -- they are latency chains of length m either way.
+// Entries of M outside the pattern of A A' are structural zeros; tiles inside the block fill hold
+// explicit zeros where the scalar fill has none, which changes nothing in the arithmetic.
+#pragma once
+
+namespace pb200 {
+
+constexpr int BAR_TILES = 9;      // named barrier of the panel elimination (ids 1..8: ipm_factor.cuh)
+constexpr int RED_TW = 160;       // [8]  unscaled diagonal-tile column (W.red scratch, ipm_factor.cuh uses < 192)
+constexpr int RED_TR = 168;       // [16] per-warp maxima
+
+// M = A diag(d) A' scattered into the tiles (zero fill first); rows m .. 8 nbk - 1 of the last
+// block get a unit diagonal so that the padded system factors trivially.
+static __device__ __forceinline__ void tiles_form_M(const Matrix& A, Work& W) {
+  const int tid = threadIdx.x;
+  double* __restrict__ Lt = W.L;
+  {
+    double2* L2 = reinterpret_cast<double2*>(Lt);
+    const size_t n2 = (size_t)A.ntiles * 32;
+    for (size_t e = tid; e < n2; e += NT) L2[e] = make_double2(0.0, 0.0);
+  }
+  __syncthreads();
+  for (int e0 = tid; e0 < A.nme; e0 += 4 * NT) {
+    int t0[4], t1[4], pos[4], k[4];
+    double w[4], s[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int e = min(e0 + q * NT, A.nme - 1);
+      t0[q] = A.me_ptr[e]; t1[q] = A.me_ptr[e + 1];
+      pos[q] = A.me_pos[e];
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) { k[q] = A.mt_k[t0[q]]; w[q] = A.mt_w[t0[q]]; }   // every entry has >= 1 term
+#pragma unroll
+    for (int q = 0; q < 4; q++) s[q] = w[q] * W.d[k[q]];
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+      for (int t = t0[q] + 1; t < t1[q]; t++) s[q] += A.mt_w[t] * W.d[A.mt_k[t]];
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+      if (e0 + q * NT < A.nme) Lt[pos[q]] = s[q];
+  }
+  const int mp = 8 * A.nbk;
+  for (int i = A.m + tid; i < mp; i += NT) Lt[(size_t)A.tl_colptr[i >> 3] * 64 + (i & 7) * 9] = 1.0;
+}
+
+// max_i |M_ii| (ldl.cl:280-294) from the diagonal tiles
+static __device__ __forceinline__ double tiles_diag_absmax(const Matrix& A, Work& W) {
+  double bmax = 0.0;
+  for (int i = threadIdx.x; i < A.m; i += NT)
+    bmax = fmax(bmax, fabs(W.L[(size_t)A.tl_colptr[i >> 3] * 64 + (i & 7) * 9]));
+  return block_max(bmax, W.red);
+}
+
+static __device__ __forceinline__ void tiles_factor(const Matrix& A, Work& W, double beta, double delta) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = warp_id();
+  const int g = lane >> 2, tg = lane & 3;
+  double* __restrict__ Lt = W.L;
+  double* __restrict__ D = W.D;
+  double* wsm = W.red + RED_TW;
+  double* rsm = W.red + RED_TR;
+  const double inv_beta = 1.0 / beta;
+  for (int J = 0; J < A.nbk; J++) {
+    const int c0 = A.tl_colptr[J], c1 = A.tl_colptr[J + 1];
+    // ---- A. left-looking tile updates ----
+    for (int t = c0 + warp; t < c1; t += NWARP) {
+      int p = A.tl_updptr[t];
+      const int p1 = A.tl_updptr[t + 1];
+      if (p == p1) continue;
+      double x0 = 0.0, x1 = 0.0, y0 = 0.0, y1 = 0.0;
+      // fragments of the current pair are loaded one pair ahead of their DMMAs
+      int a = A.tl_upda[p], b = A.tl_updb[p];
+      int K = A.tl_col[a];
+      double a1 = Lt[(size_t)a * 64 + tg * 8 + g], a2 = Lt[(size_t)a * 64 + (tg + 4) * 8 + g];
+      double b1 = Lt[(size_t)b * 64 + tg * 8 + g] * D[8 * K + tg];
+      double b2 = Lt[(size_t)b * 64 + (tg + 4) * 8 + g] * D[8 * K + tg + 4];
+      for (p++; p < p1; p++) {
+        a = A.tl_upda[p]; b = A.tl_updb[p];
+        K = A.tl_col[a];
+        const double n1 = Lt[(size_t)a * 64 + tg * 8 + g], n2 = Lt[(size_t)a * 64 + (tg + 4) * 8 + g];
+        const double m1 = Lt[(size_t)b * 64 + tg * 8 + g] * D[8 * K + tg];
+        const double m2 = Lt[(size_t)b * 64 + (tg + 4) * 8 + g] * D[8 * K + tg + 4];
+        dmma884(x0, x1, a1, b1);
+        dmma884(y0, y1, a2, b2);
+        a1 = n1; a2 = n2; b1 = m1; b2 = m2;
+      }
+      dmma884(x0, x1, a1, b1);
+      dmma884(y0, y1, a2, b2);
+      double* T = Lt + (size_t)t * 64;
+      const double v0 = T[(2 * tg) * 8 + g], v1 = T[(2 * tg + 1) * 8 + g];
+      T[(2 * tg) * 8 + g] = v0 - (x0 + y0);
+      T[(2 * tg + 1) * 8 + g] = v1 - (x1 + y1);
+    }
+    __syncthreads();
+    // ---- B. the eight columns, one at a time, over all rows of the block column ----
+    const int rows = 8 * (c1 - c0);
+    const int nthr = min(NT, (rows + 31) & ~31);
+    if (tid < nthr) {
+      const int nw = nthr >> 5;
+      double* Tc = Lt + (size_t)c0 * 64;             // the tiles of this block column are contiguous
+#pragma unroll 1
+      for (int jj = 0; jj < 8; jj++) {
+        if (tid < 8) wsm[tid] = Tc[jj * 8 + tid];    // unscaled c_{j' j} of the diagonal tile (rows j' > jj are used)
+        double th = 0.0;
+        for (int R = tid; R < rows; R += nthr)
+          if (R > jj) th = fmax(th, fabs(Tc[(size_t)(R >> 3) * 64 + jj * 8 + (R & 7)]));
+        th = warp_max(th);
+        if (lane == 0) rsm[warp] = th;
+        nbar_sync(BAR_TILES, nthr);
+        double theta = 0.0;
+        for (int w = 0; w < nw; w++) theta = fmax(theta, rsm[w]);
+        const double q = theta * inv_beta;
+        const double Dj = fmax(fabs(wsm[jj]), fmax(q * q, delta));        // ldl.cl:368 / :479
+        double wj[8];
+#pragma unroll
+        for (int j2 = 0; j2 < 8; j2++) wj[j2] = wsm[j2];
+        for (int R = tid; R < rows; R += nthr) {
+          double* pr = Tc + (size_t)(R >> 3) * 64 + (R & 7);
+          if (R > jj) {
+            const double l = pr[jj * 8] / Dj;
+            pr[jj * 8] = l;
+            const int jmax = (R < 8) ? R : 7;        // diagonal tile: lower triangle only
+#pragma unroll
+            for (int j2 = 1; j2 < 8; j2++)
+              if (j2 > jj && j2 <= jmax) pr[j2 * 8] -= l * wj[j2];
+          } else if (R == jj) {
+            pr[jj * 8] = 1.0;
+            if (8 * J + jj < A.m) D[8 * J + jj] = Dj;
+          }
+        }
+        nbar_sync(BAR_TILES, nthr);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// S <- (L D)^-1 RHS  (first half of ldl.cl:540-574), column-oriented, one warp
+static __device__ __forceinline__ void tiles_forward(const Matrix& A, Work& W, const double* rhs) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = warp_id();
+  const int m = A.m;
+  const double* __restrict__ Lt = W.L;
+  double* S = W.S;
+  if (rhs != S)
+    for (int i = tid; i < m; i += NT) S[i] = rhs[i];
+  __syncthreads();
+  if (warp == 0) {
+    const unsigned FULL = 0xffffffffu;
+    const int r = lane & 7, slot = lane >> 3;
+    for (int J = 0; J < A.nbk; J++) {
+      const int c0 = A.tl_colptr[J], c1 = A.tl_colptr[J + 1];
+      const double* Td = Lt + (size_t)c0 * 64;
+      double lcol[7];
+#pragma unroll
+      for (int jj = 0; jj < 7; jj++) lcol[jj] = Td[jj * 8 + r];      // L(r, jj), used for r > jj
+      const int row = 8 * J + r;
+      double s = (row < m) ? S[row] : 0.0;
+#pragma unroll
+      for (int jj = 0; jj < 7; jj++) {
+        const double sj = __shfl_sync(FULL, s, jj);
+        if (r > jj) s = fma(-lcol[jj], sj, s);
+      }
+      if (lane < 8 && row < m) S[row] = s;
+      double sb[8];
+#pragma unroll
+      for (int jj = 0; jj < 8; jj++) sb[jj] = __shfl_sync(FULL, s, jj);
+      for (int t = c0 + 1 + slot; t < c1; t += 4) {
+        const double* T = Lt + (size_t)t * 64;
+        double acc = 0.0;
+#pragma unroll
+        for (int jj = 0; jj < 8; jj++) acc = fma(T[jj * 8 + r], sb[jj], acc);
+        const int ri = 8 * A.tl_row[t] + r;
+        if (ri < m) S[ri] -= acc;
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < m; i += NT) S[i] /= W.D[i];
+  __syncthreads();
+}
+
+// S <- L^-T S ; dy += sign S  (second half of ldl.cl:540-574), one warp
+static __device__ __forceinline__ void tiles_backward(const Matrix& A, Work& W, double sign = 1.0) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = warp_id();
+  const int m = A.m;
+  const double* __restrict__ Lt = W.L;
+  double* S = W.S;
+  if (warp == 0) {
+    const unsigned FULL = 0xffffffffu;
+    const int c = lane & 7, slot = lane >> 3;
+    for (int J = A.nbk - 1; J >= 0; J--) {
+      const int c0 = A.tl_colptr[J], c1 = A.tl_colptr[J + 1];
+      const double* Td = Lt + (size_t)c0 * 64;
+      double part = 0.0;
+      for (int t = c0 + 1 + slot; t < c1; t += 4) {
+        const double* T = Lt + (size_t)t * 64 + c * 8;
+        const int r0 = 8 * A.tl_row[t];
+#pragma unroll
+        for (int rr = 0; rr < 8; rr++) {
+          const double sv = (r0 + rr < m) ? S[r0 + rr] : 0.0;
+          part = fma(T[rr], sv, part);
+        }
+      }
+      part += __shfl_xor_sync(FULL, part, 8);
+      part += __shfl_xor_sync(FULL, part, 16);
+      double lrow[8];
+#pragma unroll
+      for (int jj = 1; jj < 8; jj++) lrow[jj] = Td[c * 8 + jj];        // L(jj, c), used for jj > c
+      const int row = 8 * J + c;
+      double s = ((row < m) ? S[row] : 0.0) - part;
+#pragma unroll
+      for (int jj = 7; jj >= 1; jj--) {
+        const double sj = __shfl_sync(FULL, s, jj);
+        if (c < jj) s = fma(-lrow[jj], sj, s);
+      }
+      if (lane < 8 && row < m) S[row] = s;
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < m; i += NT) W.dy[i] += sign * S[i];
+  __syncthreads();
+}
+
+// factor + solve on the tile pattern (sparse_solve_primal_normal, ldl.cl:655-712: no refinement)
+static __device__ __noinline__ void solve_normal_tiles(const Matrix& A, Work& W, const Params& p) {
+  const int m = A.m, tid = threadIdx.x;
+  long long t0 = phase_begin(W);
+  tiles_form_M(A, W);
+  for (int i = tid; i < m; i += NT) W.dy[i] = 0.0;
+  __syncthreads();
+  phase_end(W, 1, t0);
+  t0 = phase_begin(W);
+  const double beta = sqrt(tiles_diag_absmax(A, W));
+  tiles_factor(A, W, beta, p.ldl_delta);
+  phase_end(W, 2, t0);
+  t0 = phase_begin(W);
+  tiles_forward(A, W, W.RHS);
+  tiles_backward(A, W);
+  phase_end(W, 3, t0);
+}
+
+}  // namespace pb200

@@ -64,6 +64,13 @@ struct Matrix {
   int nme;
   const int *me_ptr, *me_i, *me_j, *mt_k;
   const double* mt_w;
+  // tile-sparse numeric factor (ipm_tiles.cuh): L stored as the 8x8 tiles of the symbolic block
+  // fill pattern, memory ~ nnz(L).  Block column J owns tiles tl_colptr[J] .. tl_colptr[J+1]-1
+  // (diagonal tile first, then block rows ascending); element (r, c) of tile t lives at
+  // 64 t + 8 c + r.  Target tile t receives  - L(tl_upda[p]) D L(tl_updb[p])'  for
+  // p in [tl_updptr[t], tl_updptr[t+1]).  me_pos[e]: where entry e of the pattern of A A' goes.
+  int tiles, nbk, ntiles;
+  const int *tl_colptr, *tl_row, *tl_col, *tl_updptr, *tl_upda, *tl_updb, *me_pos;
 };
 
 // doubles of the shared work area W.P: two panel-multiplier tables + split-K partials

@@ -43,3 +43,26 @@ def sparse_equality_arrays(m, n0, density, nproblems, seed=0):
     A = hstack([A0, identity(m, format="csr")], format="csr")
     c = np.concatenate([c0, np.zeros((nproblems, m))], axis=1)
     return A, b, c
+
+
+def staircase_equality_arrays(m, n0, band, per_col, nproblems, seed=0):
+    """A genuinely sparse LP whose normal-equations factor stays sparse without reordering:
+    column k of ``A0`` has ``per_col`` non-zeros U(0, 1) in the rows of a window of ``band`` rows
+    centred on ``k m / n0`` (a multi-period / staircase structure), so ``A0 A0'`` is banded and
+    so is its LDL' factor.  Returns CSR ``A = [A0 I]``, ``b`` (N, m), ``c = [c0 0]`` (N, n0+m)."""
+    from scipy.sparse import csr_matrix, identity, hstack
+    rng = np.random.RandomState(seed)
+    rows, cols, vals = [], [], []
+    for k in range(n0):
+        centre = int(k * m / float(n0))
+        lo = max(0, min(m - band, centre - band // 2))
+        r = lo + rng.choice(min(band, m), size=min(per_col, band, m), replace=False)
+        rows.extend(r.tolist())
+        cols.extend([k] * len(r))
+        vals.extend(rng.rand(len(r)).tolist())
+    A0 = csr_matrix((vals, (rows, cols)), shape=(m, n0))
+    b = 0.5 + rng.rand(nproblems, m)
+    c0 = 0.5 + rng.rand(nproblems, n0)
+    A = hstack([A0, identity(m, format="csr")], format="csr")
+    c = np.concatenate([c0, np.zeros((nproblems, m))], axis=1)
+    return A, b, c

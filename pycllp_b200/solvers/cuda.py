@@ -62,6 +62,8 @@ class _CudaPrimalNormalBase(BaseSolver):
         self.engine = Engine(self.device)
         params = dict(params)
         self._preset = params.pop("preset", self._preset)
+        # sparse path only: 'auto' | 'tiles' (L on its symbolic fill pattern) | 'dense'
+        self._factor = params.pop("factor", "auto")
         self._params = params
         self._span = None
         self._out = None
@@ -76,7 +78,7 @@ class _CudaPrimalNormalBase(BaseSolver):
         self._span = (lo, hi, world, rank)
         nlocal = max(hi - lo, 1)
         if self._sparse:
-            self.engine.setup_sparse(lp.A.tocsr(), nlocal)
+            self.engine.setup_sparse(lp.A.tocsr(), nlocal, factor=self._factor)
         else:
             self.engine.setup_dense(np.asarray(lp.A.todense(), dtype=DTYPE), nlocal)
         if self._preset != "cl":
@@ -172,7 +174,9 @@ class CudaDensePrimalNormalSolver(_CudaPrimalNormalBase):
 class CudaSparsePrimalNormalSolver(_CudaPrimalNormalBase):
     """Sparse-A path (reference ``ClSparsePrimalNormalSolver``, ``cl.py:127-278``):
     CSR mat-vecs, M formed on the shared pattern of A A', no iterative refinement
-    (``ldl.cl:698-711``)."""
+    (``ldl.cl:698-711``).  ``factor='tiles'`` (or 'auto' with a sparse enough fill) computes and
+    stores L on its symbolic pattern only -- the batched counterpart of
+    ``sparse_factor_primal_normal`` (``ldl.cl:381-502``); ``engine.sparse_info()`` reports it."""
     name = 'cl_sparse_primal_normal'
     _sparse = True
 
