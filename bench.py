@@ -47,6 +47,9 @@ WORKLOADS = {
     "cfg5": dict(m=500, n0=500, density=1.0, batch=8192),
     "cfg1": dict(m=50, n0=50, density=0.1, batch=64),
     "cfg4": dict(m=2000, n0=3000, density=0.01, batch=1024, sparse=True),
+    # not a BASELINE.json config: a genuinely sparse LP (staircase structure, L < 2 % dense) for the
+    # tile-sparse numeric factor; the dense kernels would need 144 MB of factor per LP
+    "stair": dict(m=6000, n0=9000, density=4.0 / 48, batch=1024, sparse=True, band=48, per_col=4),
 }
 METRIC = "batched_lp_solves_per_sec"
 STRONG_TOTAL = 65536        # BASELINE.json configs[4]: "batch 65536 sharded across 1/2/4/8 B200"
@@ -58,6 +61,13 @@ def make_problem(name, seed_offset, batch=None):
     w = WORKLOADS[name]
     m, n0 = w["m"], w["n0"]
     N = batch or w["batch"]
+    if "band" in w:
+        from pycllp_b200.problems import staircase_equality_arrays
+        A = staircase_equality_arrays(m, n0, w["band"], w["per_col"], 1, seed=0)[0]
+        rng = np.random.RandomState(1000 + seed_offset)
+        b = 0.5 + rng.rand(N, m)
+        c = np.concatenate([0.5 + rng.rand(N, n0), np.zeros((N, m))], axis=1)
+        return A, b, c
     np.random.seed(0)
     A0 = rand(m, n0, density=w["density"]).toarray()
     rng = np.random.RandomState(1000 + seed_offset)
@@ -67,14 +77,20 @@ def make_problem(name, seed_offset, batch=None):
     return A, b, c
 
 
-def flops_per_iteration(m, n, A=None):
+def flops_per_iteration(m, n, A=None, tile_info=None):
     """M = A D A' lower triangle (m^2 n) + LDL' (m^3/3) + one forward/back
     solve (2 m^2) + the four mat-vecs with A (8 m n).  Sparse A: M costs 2 sum_k c_k(c_k+1)/2
     (c_k = non-zeros of column k), the mat-vecs 8 nnz(A); the factor of A A' is ~dense at the
     config-4 shape and is counted as m^3/3."""
     if A is not None:
-        ck = (A != 0).sum(axis=0).astype(np.float64)
-        return float((ck * (ck + 1)).sum()) + m ** 3 / 3.0 + 2.0 * m * m + 8.0 * float((A != 0).sum())
+        ck = np.asarray((A != 0).sum(axis=0)).ravel().astype(np.float64)
+        nnz = float(ck.sum())
+        if tile_info and tile_info["factor"] == "tiles":
+            # tile-sparse factor: 2 x 8^3 per tile-pair update, 2 x 8 per entry of L in the panel
+            # elimination and 4 per entry in the two triangular solves
+            fac = 1024.0 * tile_info["update_pairs"] + 20.0 * tile_info["factor_doubles"]
+            return float((ck * (ck + 1)).sum()) + fac + 8.0 * nnz
+        return float((ck * (ck + 1)).sum()) + m ** 3 / 3.0 + 2.0 * m * m + 8.0 * nnz
     return m * m * n + m ** 3 / 3.0 + 2.0 * m * m + 8.0 * m * n
 
 
@@ -126,6 +142,8 @@ def cpu_reference_rate(A, b, c, nproblems, threads, sparse=False, force_port=Fal
         impl, kind = Reference(), "reference"
     else:
         impl, kind = Oracle(), "port"
+    if hasattr(A, "toarray"):
+        A = A.toarray()
     t0 = time.perf_counter()
     solve = impl.solve_sparse if sparse else impl.solve_dense
     r = solve(A, b[:nproblems], c[:nproblems], nthreads=threads)
@@ -191,9 +209,11 @@ class DeviceRun(object):
         self.dev = torch.device("cuda", local)
         self.eng = Engine(local)
         t0 = time.perf_counter()
+        self.tile_info = None
         if self.sparse:
             from scipy.sparse import csr_matrix
             self.eng.setup_sparse(csr_matrix(self.A), N)
+            self.tile_info = self.eng.sparse_info()
         else:
             self.eng.setup_dense(self.A, N)
         self.setup_s = time.perf_counter() - t0
@@ -246,7 +266,7 @@ class DeviceRun(object):
     def roofline(self, timing, peak, peak_src):
         """achieved = algorithmic flops of one launch / its CUDA-event duration (this rank's launches:
         sum of Newton steps over the world / world ranks)."""
-        flops = flops_per_iteration(self.m, self.n, self.A if self.sparse else None) * \
+        flops = flops_per_iteration(self.m, self.n, self.A if self.sparse else None, self.tile_info) * \
             (timing["total_iters"] / self.world)
         ms_kernel = float(np.mean(timing["step_ms"]))
         achieved = flops / (ms_kernel * 1e-3) / 1e12
@@ -423,7 +443,8 @@ def main():
                        "exchange": ("one all_gather_into_tensor of %d B records per LP inside the timed step"
                                     % (run.width * 8)) if world > 1 else "none (1 rank)",
                        "gather_bytes_per_rank": (world * N * run.width * 8) if world > 1 else 0,
-                       "setup_s": run.setup_s},
+                       "setup_s": run.setup_s,
+                       **({"sparse_factor": run.tile_info} if run.tile_info else {})},
             "clocks": clocks,
             "e2e": {"value": world * N * args.steps / e2e_s, "unit": "solves/s",
                     "through": "lp.solve(solver_registry[...]) with numpy lp.b / lp.c (plugin API)",

@@ -184,6 +184,18 @@ int pycllp_b200_solve_primal_normal(pycllp_b200_engine *e, int N, const double *
 int pycllp_b200_ldl(pycllp_b200_engine *e, int N, int m, const double *AA, double *L, double *D,
                     int modified, double beta, double delta);
 
+/* Kernel-level hook: modified LDL' of N symmetric m x m matrices ON A GIVEN SPARSE PATTERN -- the
+ * reference's prototype sparse_ldl.modified_ldl (sparse_ldl.py:72-152; tests/test_ldl.py:92-108)
+ * and the factor loop of sparse_factor_primal_normal (ldl.cl:422-500), run by the tile-sparse
+ * factor.  Lindptr[m+1] / Lindices[nnz]: CSR of the LOWER pattern of L, diagonal LAST in every
+ * row (what cl.py:185-196 builds from tril(csr(L))); the pattern must be closed under
+ * elimination, as that one is.  HOST buffers: AA (N, m, m) row-major in (entries outside the
+ * pattern are not read); Ldata (N, nnz) in the order of Lindices (unit diagonal) and D (N, m) out.
+ * beta <= 0: beta = sqrt(max |diag|) as the prototype does.  Needs no setup. */
+int pycllp_b200_sparse_ldl(pycllp_b200_engine *e, int N, int m, const int *Lindptr,
+                           const int *Lindices, const double *AA, double *Ldata, double *D,
+                           double beta, double delta);
+
 /* Profiling aid: per-phase SM cycle counters summed over blocks (thread 0 of each block,
  * clock64). enable != 0 switches counting on (and zeroes the counters), 0 switches it off;
  * out16 (may be NULL, 16 entries) receives the counters accumulated since the previous call:

@@ -26,7 +26,8 @@ EXPORTS = (
     "pycllp_b200_info", "pycllp_b200_phase_profile", "pycllp_b200_set_preset",
     "pycllp_b200_solve_host_ex", "pycllp_b200_solve_device_ex", "pycllp_b200_host_alloc",
     "pycllp_b200_host_free", "pycllp_b200_host_register", "pycllp_b200_host_unregister",
-    "pycllp_b200_solve_device_packed", "pycllp_b200_fp64_probe",
+    "pycllp_b200_solve_device_packed", "pycllp_b200_fp64_probe", "pycllp_b200_set_sparse_factor",
+    "pycllp_b200_sparse_info", "pycllp_b200_tile_analysis", "pycllp_b200_sparse_ldl",
 )
 
 
@@ -85,6 +86,8 @@ def load_library():
     lib.pycllp_b200_phase_profile.argtypes = [_vp, ctypes.c_int, ctypes.POINTER(ctypes.c_ulonglong)]
     lib.pycllp_b200_tile_analysis.argtypes = [ctypes.c_int, ctypes.c_int, _ip, _ip, _ip, _ip,
                                               ctypes.POINTER(ctypes.c_longlong)] + [_ip] * 6
+    lib.pycllp_b200_sparse_ldl.argtypes = [_vp, ctypes.c_int, ctypes.c_int, _ip, _ip, _dp, _dp, _dp,
+                                           ctypes.c_double, ctypes.c_double]
     lib.pycllp_b200_set_sparse_factor.argtypes = [_vp, ctypes.c_int]
     lib.pycllp_b200_sparse_info.argtypes = [_vp, _ip, ctypes.POINTER(ctypes.c_longlong),
                                             ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_longlong),
@@ -338,6 +341,20 @@ class Engine(object):
         D = np.empty((N, m))
         self._check(self._lib.pycllp_b200_ldl(self._h, N, m, _d(AA), _d(L), _d(D), int(modified),
                                               float(beta), float(delta)), "pycllp_b200_ldl")
+        return L, D
+
+    def sparse_ldl(self, AA, indptr, indices, beta=0.0, delta=1e-6):
+        """Modified LDL' on a given CSR-lower pattern (diagonal last per row): (Ldata (N, nnz), D (N, m))."""
+        AA = _f64(AA)
+        if AA.ndim == 2:
+            AA = AA[None]
+        N, m, _ = AA.shape
+        indptr = np.ascontiguousarray(indptr, dtype=np.int32)
+        indices = np.ascontiguousarray(indices, dtype=np.int32)
+        L = np.empty((N, len(indices)))
+        D = np.empty((N, m))
+        self._check(self._lib.pycllp_b200_sparse_ldl(self._h, N, m, _i(indptr), _i(indices), _d(AA), _d(L), _d(D),
+                                                     float(beta), float(delta)), "pycllp_b200_sparse_ldl")
         return L, D
 
     def phase_profile(self, enable=True):

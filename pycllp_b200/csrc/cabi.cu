@@ -549,6 +549,11 @@ static int setup_sparse_impl(pycllp_b200_engine* e, int m, int n, const int* ind
       if ((rc = upload(e, ts.updptr, &M.tl_updptr))) return rc;
       if ((rc = upload(e, ts.upda, &M.tl_upda))) return rc;
       if ((rc = upload(e, ts.updb, &M.tl_updb))) return rc;
+      {
+        std::vector<int> updk(ts.upda.size());
+        for (size_t q = 0; q < updk.size(); q++) updk[q] = ts.col[ts.upda[q]];
+        if ((rc = upload(e, updk, &M.tl_updk))) return rc;
+      }
       if ((rc = upload(e, ts.me_pos, &M.me_pos))) return rc;
     }
   }
@@ -779,6 +784,83 @@ int pycllp_b200_ldl(pycllp_b200_engine* e, int N, int m, const double* AA, doubl
   cudaFree(d_AA); cudaFree(d_L); cudaFree(d_D); cudaFree(d_s);
   if (err != cudaSuccess) return fail(e, PYCLLP_B200_ERR_CUDA, cudaGetErrorString(err));
   return 0;
+}
+
+static int sparse_ldl_impl(pycllp_b200_engine* e, int N, int m, const int* indptr, const int* indices,
+                           const double* AA, double* Ldata, double* D, double beta, double delta) {
+  if (indptr[0] != 0) return fail(e, PYCLLP_B200_ERR_ARG, "sparse_ldl: indptr[0] != 0");
+  for (int i = 0; i < m; i++)
+    if (indptr[i + 1] <= indptr[i])
+      return fail(e, PYCLLP_B200_ERR_ARG, "sparse_ldl: every row needs its diagonal entry");
+  const int nnz = indptr[m];
+  std::vector<int> pi(nnz), pj(nnz);
+  for (int i = 0; i < m; i++) {
+    for (int k = indptr[i]; k < indptr[i + 1]; k++) {
+      if (indices[k] < 0 || indices[k] > i)
+        return fail(e, PYCLLP_B200_ERR_ARG, "sparse_ldl: pattern must be lower triangular");
+      pi[k] = i; pj[k] = indices[k];
+    }
+    if (indices[indptr[i + 1] - 1] != i)
+      return fail(e, PYCLLP_B200_ERR_ARG, "sparse_ldl: the diagonal must be the last entry of its row");
+  }
+  TileSym ts;
+  if (!tile_symbolic(m, pi, pj, (size_t)INT_MAX / 64, ts))
+    return fail(e, PYCLLP_B200_ERR_ARG, "sparse_ldl: tile structure exceeds 32-bit positions");
+  DeviceGuard guard(e->device);
+  Matrix M{};
+  M.m = m; M.tiles = 1; M.nbk = ts.nbk; M.ntiles = ts.ntiles;
+  std::vector<int> updk(ts.upda.size());
+  for (size_t q = 0; q < updk.size(); q++) updk[q] = ts.col[ts.upda[q]];
+  std::vector<void*> allocs;
+  auto up = [&](const std::vector<int>& h, const int** out) -> cudaError_t {
+    int* d = nullptr;
+    cudaError_t er = cudaMalloc(&d, std::max<size_t>(h.size(), 1) * sizeof(int));
+    if (er != cudaSuccess) return er;
+    allocs.push_back(d);
+    *out = d;
+    return h.empty() ? cudaSuccess : cudaMemcpy(d, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice);
+  };
+  const int *d_pi = nullptr, *d_pj = nullptr;
+  cudaError_t err = up(ts.colptr, &M.tl_colptr);
+  if (err == cudaSuccess) err = up(ts.row, &M.tl_row);
+  if (err == cudaSuccess) err = up(ts.col, &M.tl_col);
+  if (err == cudaSuccess) err = up(ts.updptr, &M.tl_updptr);
+  if (err == cudaSuccess) err = up(ts.upda, &M.tl_upda);
+  if (err == cudaSuccess) err = up(ts.updb, &M.tl_updb);
+  if (err == cudaSuccess) err = up(updk, &M.tl_updk);
+  if (err == cudaSuccess) err = up(ts.me_pos, &M.me_pos);
+  if (err == cudaSuccess) err = up(pi, &d_pi);
+  if (err == cudaSuccess) err = up(pj, &d_pj);
+  const size_t slot = al16((size_t)ts.ntiles * 64 + 8 * (size_t)ts.nbk);
+  const int grid = std::min(N, e->num_sms);
+  double *d_AA = nullptr, *d_L = nullptr, *d_D = nullptr, *d_s = nullptr;
+  if (err == cudaSuccess) err = cudaMalloc(&d_AA, (size_t)N * m * m * sizeof(double));
+  if (err == cudaSuccess) err = cudaMalloc(&d_L, (size_t)N * nnz * sizeof(double));
+  if (err == cudaSuccess) err = cudaMalloc(&d_D, (size_t)N * m * sizeof(double));
+  if (err == cudaSuccess) err = cudaMalloc(&d_s, slot * grid * sizeof(double));
+  cudaStream_t s = e->stream;
+  if (err == cudaSuccess)
+    err = cudaMemcpyAsync(d_AA, AA, (size_t)N * m * m * sizeof(double), cudaMemcpyHostToDevice, s);
+  if (err == cudaSuccess) {
+    err = launch_tiles_hook(M, N, nnz, d_pi, d_pj, d_AA, d_L, d_D, beta, delta, d_s, slot, grid, s);
+    e->launches += 1;
+  }
+  if (err == cudaSuccess) err = cudaMemcpyAsync(Ldata, d_L, (size_t)N * nnz * sizeof(double), cudaMemcpyDeviceToHost, s);
+  if (err == cudaSuccess) err = cudaMemcpyAsync(D, d_D, (size_t)N * m * sizeof(double), cudaMemcpyDeviceToHost, s);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(s);
+  cudaStreamSynchronize(s);
+  cudaFree(d_AA); cudaFree(d_L); cudaFree(d_D); cudaFree(d_s);
+  for (void* p : allocs) cudaFree(p);
+  if (err != cudaSuccess) return fail(e, PYCLLP_B200_ERR_CUDA, cudaGetErrorString(err));
+  return 0;
+}
+
+int pycllp_b200_sparse_ldl(pycllp_b200_engine* e, int N, int m, const int* Lindptr, const int* Lindices,
+                           const double* AA, double* Ldata, double* D, double beta, double delta) {
+  if (!e) return PYCLLP_B200_ERR_ARG;
+  if (N <= 0 || m <= 0 || !Lindptr || !Lindices || !AA || !Ldata || !D)
+    return fail(e, PYCLLP_B200_ERR_ARG, "sparse_ldl: bad argument");
+  return guarded(e, [&] { return sparse_ldl_impl(e, N, m, Lindptr, Lindices, AA, Ldata, D, beta, delta); });
 }
 
 int pycllp_b200_phase_profile(pycllp_b200_engine* e, int enable, unsigned long long* out16) {

@@ -14,6 +14,9 @@ cudaError_t launch_solve(const Matrix& A, const Batch& B, const Scratch& sc, con
                          int grid, size_t smem_bytes, cudaStream_t stream);
 cudaError_t launch_solve_py(const Matrix& A, const Batch& B, const Scratch& sc, const Params& p,
                             int grid, size_t smem_bytes, cudaStream_t stream);
+cudaError_t launch_tiles_hook(const Matrix& A, int N, int nnz, const int* pat_i, const int* pat_j,
+                              const double* AA, double* Ldata, double* D, double beta, double delta,
+                              double* scratch, size_t slot, int grid, cudaStream_t stream);
 cudaError_t launch_ldl_hook(int N, int m, const double* AA, double* L, double* D, int modified,
                             double beta, double delta, double* scratch, size_t slot, int grid,
                             cudaStream_t stream);

@@ -39,6 +39,48 @@ ldl_hook_kernel(int N, int m, const double* AA, double* Lout, double* Dout, int 
   }
 }
 
+// Modified LDL' of given symmetric matrices ON A GIVEN SPARSE PATTERN -- the reference's prototype
+// sparse_ldl.modified_ldl (sparse_ldl.py:72-152; the device twin is the factor loop of
+// sparse_factor_primal_normal, ldl.cl:422-500), test hook of the tile-sparse factor.
+// pat_i / pat_j: the nnz pattern entries (CSR-lower order, diagonal last in each row);
+// A.me_pos[k]: where entry k lives in the tile storage.  Ldata (N, nnz) / D (N, m) out.
+__global__ void __launch_bounds__(NT, 1)
+tiles_hook_kernel(Matrix A, int N, int nnz, const int* pat_i, const int* pat_j, const double* AA,
+                  double* Ldata, double* Dout, double beta_in, double delta, double* scratch, size_t slot) {
+  extern __shared__ __align__(16) double smem[];
+  Work W;
+  W.red = smem;
+  W.fb = smem + RED_SIZE;
+  W.L = scratch + (size_t)blockIdx.x * slot;
+  W.D = W.L + (size_t)A.ntiles * 64;
+  W.prof = nullptr;
+  const int m = A.m, tid = threadIdx.x;
+  for (int q = blockIdx.x; q < N; q += gridDim.x) {
+    const double* Aq = AA + (size_t)q * m * m;
+    for (size_t e = tid; e < (size_t)A.ntiles * 64; e += NT) W.L[e] = 0.0;
+    __syncthreads();
+    for (int k = tid; k < nnz; k += NT) W.L[A.me_pos[k]] = Aq[(size_t)pat_i[k] * m + pat_j[k]];
+    for (int i = m + tid; i < 8 * A.nbk; i += NT) W.L[(size_t)A.tl_colptr[i >> 3] * 64 + (i & 7) * 9] = 1.0;
+    __syncthreads();
+    const double beta = beta_in > 0.0 ? beta_in : sqrt(tiles_diag_absmax(A, W));   // sparse_ldl.py:86
+    tiles_factor(A, W, beta, delta);
+    for (int k = tid; k < nnz; k += NT)
+      Ldata[(size_t)q * nnz + k] = (pat_i[k] == pat_j[k]) ? 1.0 : W.L[A.me_pos[k]];
+    for (int i = tid; i < m; i += NT) Dout[(size_t)q * m + i] = W.D[i];
+    __syncthreads();
+  }
+}
+
+cudaError_t launch_tiles_hook(const Matrix& A, int N, int nnz, const int* pat_i, const int* pat_j,
+                              const double* AA, double* Ldata, double* D, double beta, double delta,
+                              double* scratch, size_t slot, int grid, cudaStream_t stream) {
+  const size_t smem = (size_t)(RED_SIZE + FB_DOUBLES) * sizeof(double);
+  cudaError_t err = cudaFuncSetAttribute(tiles_hook_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err != cudaSuccess) return err;
+  tiles_hook_kernel<<<grid, NT, smem, stream>>>(A, N, nnz, pat_i, pat_j, AA, Ldata, D, beta, delta, scratch, slot);
+  return cudaGetLastError();
+}
+
 // FP64 tensor-core (DMMA m8n8k4) issue-rate probe: eight independent accumulator tiles per warp,
 // nothing but DMMAs in the loop.  The roofline denominator of bench.py is measured with this
 // on the box the bench runs on (MEASURED_PEAKS.json holds only HBM and bf16).

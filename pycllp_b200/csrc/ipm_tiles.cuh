@@ -27,8 +27,8 @@
 namespace pb200 {
 
 constexpr int BAR_TILES = 9;      // named barrier of the panel elimination (ids 1..8: ipm_factor.cuh)
-constexpr int RED_TW = 160;       // [8]  unscaled diagonal-tile column (W.red scratch, ipm_factor.cuh uses < 192)
-constexpr int RED_TR = 168;       // [16] per-warp maxima
+constexpr int RED_TW = 160;       // [2][8]  unscaled diagonal-tile column, double-buffered (W.red scratch)
+constexpr int RED_TR = 176;       // [2][16] per-warp maxima                     (RED_KEEP starts at 208)
 
 // M = A diag(d) A' scattered into the tiles (zero fill first); rows m .. 8 nbk - 1 of the last
 // block get a unit diagonal so that the padded system factors trivially.
@@ -73,127 +73,203 @@ static __device__ __forceinline__ double tiles_diag_absmax(const Matrix& A, Work
   return block_max(bmax, W.red);
 }
 
+// Per-block cache of D (and of S during the solves) in the shared-memory area that the dense
+// super-panel factor would use (W.fb, FB_DOUBLES): the tile updates read D_K of every pair and
+// the solves are latency chains over S, neither should pay an L2 round trip per access.
+__device__ __forceinline__ bool tiles_cache_ok(const Matrix& A) { return 2 * 8 * A.nbk <= FB_DOUBLES; }
+
 static __device__ __forceinline__ void tiles_factor(const Matrix& A, Work& W, double beta, double delta) {
   const int tid = threadIdx.x, lane = tid & 31, warp = warp_id();
   const int g = lane >> 2, tg = lane & 3;
+  const unsigned FULL = 0xffffffffu;
   double* __restrict__ Lt = W.L;
-  double* __restrict__ D = W.D;
-  double* wsm = W.red + RED_TW;
-  double* rsm = W.red + RED_TR;
+  const bool cached = tiles_cache_ok(A);
+  double* __restrict__ D = cached ? W.fb : W.D;      // (copied to W.D at the end when cached)
+  double* wsm = W.red + RED_TW;                      // [2][8]
+  double* rsm = W.red + RED_TR;                      // [2][16]
   const double inv_beta = 1.0 / beta;
   for (int J = 0; J < A.nbk; J++) {
-    const int c0 = A.tl_colptr[J], c1 = A.tl_colptr[J + 1];
-    // ---- A. left-looking tile updates ----
+    const int c0 = __ldg(A.tl_colptr + J), c1 = __ldg(A.tl_colptr + J + 1);
+    long long tq = phase_begin(W);
+    // ---- A. left-looking tile updates: one warp per tile ----
     for (int t = c0 + warp; t < c1; t += NWARP) {
-      int p = A.tl_updptr[t];
-      const int p1 = A.tl_updptr[t + 1];
-      if (p == p1) continue;
-      double x0 = 0.0, x1 = 0.0, y0 = 0.0, y1 = 0.0;
-      // fragments of the current pair are loaded one pair ahead of their DMMAs
-      int a = A.tl_upda[p], b = A.tl_updb[p];
-      int K = A.tl_col[a];
-      double a1 = Lt[(size_t)a * 64 + tg * 8 + g], a2 = Lt[(size_t)a * 64 + (tg + 4) * 8 + g];
-      double b1 = Lt[(size_t)b * 64 + tg * 8 + g] * D[8 * K + tg];
-      double b2 = Lt[(size_t)b * 64 + (tg + 4) * 8 + g] * D[8 * K + tg + 4];
-      for (p++; p < p1; p++) {
-        a = A.tl_upda[p]; b = A.tl_updb[p];
-        K = A.tl_col[a];
-        const double n1 = Lt[(size_t)a * 64 + tg * 8 + g], n2 = Lt[(size_t)a * 64 + (tg + 4) * 8 + g];
-        const double m1 = Lt[(size_t)b * 64 + tg * 8 + g] * D[8 * K + tg];
-        const double m2 = Lt[(size_t)b * 64 + (tg + 4) * 8 + g] * D[8 * K + tg + 4];
-        dmma884(x0, x1, a1, b1);
-        dmma884(y0, y1, a2, b2);
-        a1 = n1; a2 = n2; b1 = m1; b2 = m2;
-      }
-      dmma884(x0, x1, a1, b1);
-      dmma884(y0, y1, a2, b2);
+      const int p0 = __ldg(A.tl_updptr + t), p1 = __ldg(A.tl_updptr + t + 1);
+      if (p0 == p1) continue;
       double* T = Lt + (size_t)t * 64;
-      const double v0 = T[(2 * tg) * 8 + g], v1 = T[(2 * tg + 1) * 8 + g];
+      const double v0 = T[(2 * tg) * 8 + g], v1 = T[(2 * tg + 1) * 8 + g];   // (in flight during the loop)
+      double x0 = 0.0, x1 = 0.0, y0 = 0.0, y1 = 0.0;
+      for (int base = p0; base < p1; base += 32) {
+        // the pair list of this tile, 32 pairs per round trip (one per lane), broadcast by shuffles
+        const int mine = min(base + lane, p1 - 1);
+        const int ia = __ldg(A.tl_upda + mine), ib = __ldg(A.tl_updb + mine), ik = __ldg(A.tl_updk + mine);
+        const int cnt = min(32, p1 - base);
+        for (int q = 0; q < cnt; q += 4) {
+          double fa1[4], fa2[4], fb1[4], fb2[4];
+#pragma unroll
+          for (int u = 0; u < 4; u++) {              // four pairs' fragments in flight
+            const int qq = min(q + u, cnt - 1);
+            const int a = __shfl_sync(FULL, ia, qq), b = __shfl_sync(FULL, ib, qq), K = __shfl_sync(FULL, ik, qq);
+            const double* pa = Lt + (size_t)a * 64 + tg * 8 + g;
+            const double* pb = Lt + (size_t)b * 64 + tg * 8 + g;
+            const bool on = q + u < cnt;
+            fa1[u] = on ? pa[0] : 0.0;
+            fa2[u] = on ? pa[32] : 0.0;
+            fb1[u] = pb[0] * D[8 * K + tg];
+            fb2[u] = pb[32] * D[8 * K + tg + 4];
+          }
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            dmma884(x0, x1, fa1[u], fb1[u]);
+            dmma884(y0, y1, fa2[u], fb2[u]);
+          }
+        }
+      }
       T[(2 * tg) * 8 + g] = v0 - (x0 + y0);
       T[(2 * tg + 1) * 8 + g] = v1 - (x1 + y1);
     }
     __syncthreads();
+    phase_end(W, 13, tq);                            // (profile slots of the dense factor: f_old = tile updates,
+    tq = phase_begin(W);                             //  f_solve = panel elimination)
     // ---- B. the eight columns, one at a time, over all rows of the block column ----
     const int rows = 8 * (c1 - c0);
-    const int nthr = min(NT, (rows + 31) & ~31);
-    if (tid < nthr) {
-      const int nw = nthr >> 5;
-      double* Tc = Lt + (size_t)c0 * 64;             // the tiles of this block column are contiguous
+    double* Tc = Lt + (size_t)c0 * 64;               // the tiles of this block column are contiguous
+    if (rows <= NT) {
+      // one thread per row, the row's eight entries in registers from start to finish
+      const int nthr = (rows + 31) & ~31;
+      if (tid < nthr) {
+        const int nw = nthr >> 5;
+        const bool live = tid < rows;
+        double* pr = Tc + (size_t)(tid >> 3) * 64 + (tid & 7);
+        double c[8];
+#pragma unroll
+        for (int jj = 0; jj < 8; jj++) c[jj] = live ? pr[jj * 8] : 0.0;
+        const int jmax = (tid < 8) ? tid : 7;        // diagonal tile: lower triangle only
+#pragma unroll
+        for (int jj = 0; jj < 8; jj++) {
+          double* wb = wsm + 8 * (jj & 1);
+          double* rb = rsm + 16 * (jj & 1);
+          if (tid < 8) wb[tid] = c[jj];              // unscaled c_{j' j} of the diagonal tile
+          double th = (live && tid > jj) ? fabs(c[jj]) : 0.0;
+          th = warp_max(th);
+          if (lane == 0) rb[warp] = th;
+          nbar_sync(BAR_TILES, nthr);
+          double theta = 0.0;
+          for (int w = 0; w < nw; w++) theta = fmax(theta, rb[w]);
+          const double q = theta * inv_beta;
+          const double Dj = fmax(fabs(wb[jj]), fmax(q * q, delta));        // ldl.cl:368 / :479
+          if (tid > jj) {
+            const double l = c[jj] * rcp_pos64(Dj);  // (reciprocal-multiply, <= 1 ulp from the division, as the dense factor)
+            c[jj] = l;
+#pragma unroll
+            for (int j2 = jj + 1; j2 < 8; j2++)
+              if (j2 <= jmax) c[j2] = fma(-l, wb[j2], c[j2]);
+          } else if (tid == jj) {
+            c[jj] = 1.0;
+            if (cached || 8 * J + jj < A.m) D[8 * J + jj] = Dj;
+          }
+        }
+        if (live) {
+#pragma unroll
+          for (int jj = 0; jj < 8; jj++)
+            if (jj <= jmax) pr[jj * 8] = c[jj];
+        }
+      }
+    } else {
+      // (block columns with more than NT rows: same rule, rows in memory)
 #pragma unroll 1
       for (int jj = 0; jj < 8; jj++) {
-        if (tid < 8) wsm[tid] = Tc[jj * 8 + tid];    // unscaled c_{j' j} of the diagonal tile (rows j' > jj are used)
+        if (tid < 8) wsm[tid] = Tc[jj * 8 + tid];
         double th = 0.0;
-        for (int R = tid; R < rows; R += nthr)
+        for (int R = tid; R < rows; R += NT)
           if (R > jj) th = fmax(th, fabs(Tc[(size_t)(R >> 3) * 64 + jj * 8 + (R & 7)]));
-        th = warp_max(th);
-        if (lane == 0) rsm[warp] = th;
-        nbar_sync(BAR_TILES, nthr);
-        double theta = 0.0;
-        for (int w = 0; w < nw; w++) theta = fmax(theta, rsm[w]);
+        const double theta = block_max(th, W.red);
         const double q = theta * inv_beta;
-        const double Dj = fmax(fabs(wsm[jj]), fmax(q * q, delta));        // ldl.cl:368 / :479
+        const double Dj = fmax(fabs(wsm[jj]), fmax(q * q, delta));
         double wj[8];
 #pragma unroll
         for (int j2 = 0; j2 < 8; j2++) wj[j2] = wsm[j2];
-        for (int R = tid; R < rows; R += nthr) {
+        for (int R = tid; R < rows; R += NT) {
           double* pr = Tc + (size_t)(R >> 3) * 64 + (R & 7);
           if (R > jj) {
             const double l = pr[jj * 8] / Dj;
+            const int jmax = (R < 8) ? R : 7;
+            double v[8];
+#pragma unroll
+            for (int j2 = 1; j2 < 8; j2++) v[j2] = pr[j2 * 8];     // (loads before the stores)
             pr[jj * 8] = l;
-            const int jmax = (R < 8) ? R : 7;        // diagonal tile: lower triangle only
 #pragma unroll
             for (int j2 = 1; j2 < 8; j2++)
-              if (j2 > jj && j2 <= jmax) pr[j2 * 8] -= l * wj[j2];
+              if (j2 > jj && j2 <= jmax) pr[j2 * 8] = v[j2] - l * wj[j2];
           } else if (R == jj) {
             pr[jj * 8] = 1.0;
-            if (8 * J + jj < A.m) D[8 * J + jj] = Dj;
+            if (cached || 8 * J + jj < A.m) D[8 * J + jj] = Dj;
           }
         }
-        nbar_sync(BAR_TILES, nthr);
+        __syncthreads();
       }
     }
+    __syncthreads();
+    phase_end(W, 10, tq);
+  }
+  if (cached) {
+    for (int i = tid; i < A.m; i += NT) W.D[i] = D[i];
     __syncthreads();
   }
 }
 
-// S <- (L D)^-1 RHS  (first half of ldl.cl:540-574), column-oriented, one warp
+// S <- (L D)^-1 RHS  (first half of ldl.cl:540-574), column-oriented, one warp; S is kept in
+// shared memory while the chain runs (tiles_cache_ok)
 static __device__ __forceinline__ void tiles_forward(const Matrix& A, Work& W, const double* rhs) {
   const int tid = threadIdx.x, lane = tid & 31, warp = warp_id();
-  const int m = A.m;
+  const int m = A.m, mp = 8 * A.nbk;
   const double* __restrict__ Lt = W.L;
-  double* S = W.S;
-  if (rhs != S)
+  const bool cached = tiles_cache_ok(A);
+  double* S = cached ? W.fb + mp : W.S;
+  if (cached) {
+    for (int i = tid; i < mp; i += NT) S[i] = (i < m) ? rhs[i] : 0.0;
+  } else if (rhs != S) {
     for (int i = tid; i < m; i += NT) S[i] = rhs[i];
+  }
   __syncthreads();
   if (warp == 0) {
     const unsigned FULL = 0xffffffffu;
     const int r = lane & 7, slot = lane >> 3;
+    int c0 = __ldg(A.tl_colptr);
     for (int J = 0; J < A.nbk; J++) {
-      const int c0 = A.tl_colptr[J], c1 = A.tl_colptr[J + 1];
+      const int c1 = __ldg(A.tl_colptr + J + 1);
       const double* Td = Lt + (size_t)c0 * 64;
       double lcol[7];
 #pragma unroll
       for (int jj = 0; jj < 7; jj++) lcol[jj] = Td[jj * 8 + r];      // L(r, jj), used for r > jj
+      // the first sub-diagonal tile of each slot is fetched together with the diagonal tile
+      const int t1 = c0 + 1 + slot;
+      double tl[8];
+#pragma unroll
+      for (int jj = 0; jj < 8; jj++) tl[jj] = (t1 < c1) ? Lt[(size_t)t1 * 64 + jj * 8 + r] : 0.0;
       const int row = 8 * J + r;
-      double s = (row < m) ? S[row] : 0.0;
+      double s = (cached || row < m) ? S[row] : 0.0;
 #pragma unroll
       for (int jj = 0; jj < 7; jj++) {
         const double sj = __shfl_sync(FULL, s, jj);
         if (r > jj) s = fma(-lcol[jj], sj, s);
       }
-      if (lane < 8 && row < m) S[row] = s;
+      if (lane < 8 && (cached || row < m)) S[row] = s;
       double sb[8];
 #pragma unroll
       for (int jj = 0; jj < 8; jj++) sb[jj] = __shfl_sync(FULL, s, jj);
-      for (int t = c0 + 1 + slot; t < c1; t += 4) {
-        const double* T = Lt + (size_t)t * 64;
+      for (int t = t1; t < c1; t += 4) {
+        if (t != t1) {
+#pragma unroll
+          for (int jj = 0; jj < 8; jj++) tl[jj] = Lt[(size_t)t * 64 + jj * 8 + r];
+        }
         double acc = 0.0;
 #pragma unroll
-        for (int jj = 0; jj < 8; jj++) acc = fma(T[jj * 8 + r], sb[jj], acc);
-        const int ri = 8 * A.tl_row[t] + r;
-        if (ri < m) S[ri] -= acc;
+        for (int jj = 0; jj < 8; jj++) acc = fma(tl[jj], sb[jj], acc);
+        const int ri = 8 * __ldg(A.tl_row + t) + r;
+        if (cached || ri < m) S[ri] -= acc;
       }
       __syncwarp();
+      c0 = c1;
     }
   }
   __syncthreads();
@@ -204,39 +280,45 @@ static __device__ __forceinline__ void tiles_forward(const Matrix& A, Work& W, c
 // S <- L^-T S ; dy += sign S  (second half of ldl.cl:540-574), one warp
 static __device__ __forceinline__ void tiles_backward(const Matrix& A, Work& W, double sign = 1.0) {
   const int tid = threadIdx.x, lane = tid & 31, warp = warp_id();
-  const int m = A.m;
+  const int m = A.m, mp = 8 * A.nbk;
   const double* __restrict__ Lt = W.L;
-  double* S = W.S;
+  const bool cached = tiles_cache_ok(A);
+  double* S = cached ? W.fb + mp : W.S;
   if (warp == 0) {
     const unsigned FULL = 0xffffffffu;
     const int c = lane & 7, slot = lane >> 3;
+    int c1 = __ldg(A.tl_colptr + A.nbk);
     for (int J = A.nbk - 1; J >= 0; J--) {
-      const int c0 = A.tl_colptr[J], c1 = A.tl_colptr[J + 1];
+      const int c0 = __ldg(A.tl_colptr + J);
       const double* Td = Lt + (size_t)c0 * 64;
+      double lrow[8];
+#pragma unroll
+      for (int jj = 1; jj < 8; jj++) lrow[jj] = Td[c * 8 + jj];        // L(jj, c), used for jj > c
       double part = 0.0;
       for (int t = c0 + 1 + slot; t < c1; t += 4) {
         const double* T = Lt + (size_t)t * 64 + c * 8;
-        const int r0 = 8 * A.tl_row[t];
+        const int r0 = 8 * __ldg(A.tl_row + t);
+        double tv[8];
+#pragma unroll
+        for (int rr = 0; rr < 8; rr++) tv[rr] = T[rr];
 #pragma unroll
         for (int rr = 0; rr < 8; rr++) {
-          const double sv = (r0 + rr < m) ? S[r0 + rr] : 0.0;
-          part = fma(T[rr], sv, part);
+          const double sv = (cached || r0 + rr < m) ? S[r0 + rr] : 0.0;
+          part = fma(tv[rr], sv, part);
         }
       }
       part += __shfl_xor_sync(FULL, part, 8);
       part += __shfl_xor_sync(FULL, part, 16);
-      double lrow[8];
-#pragma unroll
-      for (int jj = 1; jj < 8; jj++) lrow[jj] = Td[c * 8 + jj];        // L(jj, c), used for jj > c
       const int row = 8 * J + c;
-      double s = ((row < m) ? S[row] : 0.0) - part;
+      double s = ((cached || row < m) ? S[row] : 0.0) - part;
 #pragma unroll
       for (int jj = 7; jj >= 1; jj--) {
         const double sj = __shfl_sync(FULL, s, jj);
         if (c < jj) s = fma(-lrow[jj], sj, s);
       }
-      if (lane < 8 && row < m) S[row] = s;
+      if (lane < 8 && (cached || row < m)) S[row] = s;
       __syncwarp();
+      c1 = c0;
     }
   }
   __syncthreads();

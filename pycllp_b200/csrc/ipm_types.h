@@ -70,7 +70,7 @@ struct Matrix {
   // 64 t + 8 c + r.  Target tile t receives  - L(tl_upda[p]) D L(tl_updb[p])'  for
   // p in [tl_updptr[t], tl_updptr[t+1]).  me_pos[e]: where entry e of the pattern of A A' goes.
   int tiles, nbk, ntiles;
-  const int *tl_colptr, *tl_row, *tl_col, *tl_updptr, *tl_upda, *tl_updb, *me_pos;
+  const int *tl_colptr, *tl_row, *tl_col, *tl_updptr, *tl_upda, *tl_updb, *tl_updk, *me_pos;   // tl_updk[p]: block column K of pair p
 };
 
 // doubles of the shared work area W.P: two panel-multiplier tables + split-K partials

@@ -99,3 +99,34 @@ def test_tiles_mode_has_no_refinement(engine):
     engine.setup_sparse(A, 2, factor="dense")
     assert engine.sparse_info()["factor"] == "dense"
     engine.set_params(max_refine=3)
+
+
+def test_sparse_ldl_hook_vs_dense_modified_ldl(engine, oracle):
+    """tests/test_ldl.py:92-108 (test_sparse_modified_ldl): the modified LDL' of a sparse SPD matrix on
+    the CSR-lower pattern of its factor equals the dense modified LDL' restricted to that pattern --
+    dense side: the oracle's restatement of the reference's modified_ldl kernel (ldl.cl:57-107)."""
+    from scipy.sparse import rand as sparse_rand, tril
+    rng = np.random.RandomState(2)
+    for m, n, dens in [(50, 100, 0.025), (97, 60, 0.03), (130, 300, 0.01)]:
+        N = 3
+        AA = np.empty((N, m, m))
+        for q in range(N):
+            A = sparse_rand(m, n, density=dens, random_state=rng).toarray()
+            if q:
+                A = A * (A0 != 0)                       # same pattern, other values
+                A[A0 != 0] = rng.rand(int((A0 != 0).sum()))
+            else:
+                A0 = A
+            AA[q] = A @ A.T + 1e-3 * np.eye(m)
+        beta = float(np.sqrt(np.abs(AA[0]).max()))
+        Lp, D = oracle.ldl(AA, modified=True, beta=beta)
+        Ld = np.zeros((N, m, m))
+        il = np.tril_indices(m)
+        Ld[:, il[0], il[1]] = Lp
+        pat = tril(csr_matrix((np.abs(Ld).sum(axis=0) != 0).astype(float)), format="csr")
+        pat.sort_indices()
+        assert pat.nnz < 0.6 * m * (m + 1) // 2             # (the factor is actually sparse)
+        Ls, Ds = engine.sparse_ldl(AA, pat.indptr, pat.indices, beta=beta)
+        rows = np.repeat(np.arange(m), np.diff(pat.indptr))
+        np.testing.assert_allclose(Ds, D, rtol=1e-10)
+        np.testing.assert_allclose(Ls, Ld[:, rows, pat.indices], rtol=1e-9, atol=1e-12)

@@ -114,3 +114,24 @@ if "prof4" in which:
     print("cfg4 N=%d %.3fs (%.1f solves/s); phase cycles per Newton step:" % (N, dt, N / dt))
     for k, v in prof.items():
         print("  %-14s %10.0f cyc/step  %5.1f%%" % (k, v / steps, 100.0 * v / tot))
+
+if "proft" in which:
+    # genuinely sparse LPs (staircase structure): tile-sparse factor vs the dense packed kernels
+    from pycllp_b200.problems import staircase_equality_arrays
+    for (m, n0, band, N, modes) in [(1500, 2250, 40, 296, ("tiles", "dense")), (6000, 9000, 48, 296, ("tiles",))]:
+        A, b, c = staircase_equality_arrays(m, n0, band, 4, N, seed=0)
+        for mode in modes:
+            t = time.time(); eng.setup_sparse(A, N, factor=mode); ts = time.time() - t
+            si = eng.sparse_info()
+            eng.solve_host(b[:148], c[:148])
+            eng.phase_profile(True)
+            t = time.time(); res = eng.solve_host(b, c); dt = time.time() - t
+            prof = eng.phase_profile(False)
+            steps = res["iters"].sum()
+            tot = sum(v for k, v in prof.items() if k in ("rhs_norms", "form_M", "factor", "tri_solve", "residual", "step"))
+            print("staircase m=%d n=%d %s: setup %.2fs, N=%d %.3fs (%.1f solves/s), status0 %d, steps %.1f, factor doubles %d (dense %d), pairs %d" % (
+                m, m + n0, mode, ts, N, dt, N / dt, int((res["status"] == 0).sum()), res["iters"].mean(),
+                si["factor_doubles"], si["dense_factor_doubles"], si["update_pairs"]))
+            for k, v in prof.items():
+                if v:
+                    print("  %-14s %10.0f cyc/step  %5.1f%%" % (k, v / steps, 100.0 * v / tot))
