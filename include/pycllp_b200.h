@@ -98,6 +98,16 @@ int pycllp_b200_setup_dense(pycllp_b200_engine *e, int m, int n, const double *A
 int pycllp_b200_setup_sparse(pycllp_b200_engine *e, int m, int n, const int *indptr,
                              const int *indices, const double *data, int max_problems);
 
+/* Kernels for SMALL problems (takes effect at the next setup; default 1, env PB200_SMALL overrides):
+ *   1  dense problems with m <= 63 whose whole working set (A included) fits in ~56 KB of shared
+ *      memory run on the 128-thread kernel of csrc/ipm_small.cuh, four or more LPs per SM -- "one
+ *      warp group per problem" at the reference's own example size (examples/random_problem.py:
+ *      m = 50, n = 100); other shapes whose working set is below half an SM's shared memory run the
+ *      512-thread kernel two blocks per SM (its 64-register build);
+ *   2  only the latter;   0  neither (one 512-thread block per SM, as for the large shapes).
+ * Same algorithm, constants and results (to rounding) in every mode. */
+int pycllp_b200_set_small_kernels(pycllp_b200_engine *e, int mode);
+
 /* Numeric factor of the SPARSE path (takes effect at the next setup_sparse):
  *   1  tiles: L is stored and computed on the symbolic fill pattern only, at 8x8-tile granularity
  *      (block elimination tree + block fill analysed once per engine; memory ~ nnz(L); DMMA tile

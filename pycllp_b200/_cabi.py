@@ -28,6 +28,7 @@ EXPORTS = (
     "pycllp_b200_host_free", "pycllp_b200_host_register", "pycllp_b200_host_unregister",
     "pycllp_b200_solve_device_packed", "pycllp_b200_fp64_probe", "pycllp_b200_set_sparse_factor",
     "pycllp_b200_sparse_info", "pycllp_b200_tile_analysis", "pycllp_b200_sparse_ldl",
+    "pycllp_b200_set_small_kernels",
 )
 
 
@@ -89,6 +90,7 @@ def load_library():
     lib.pycllp_b200_sparse_ldl.argtypes = [_vp, ctypes.c_int, ctypes.c_int, _ip, _ip, _dp, _dp, _dp,
                                            ctypes.c_double, ctypes.c_double]
     lib.pycllp_b200_set_sparse_factor.argtypes = [_vp, ctypes.c_int]
+    lib.pycllp_b200_set_small_kernels.argtypes = [_vp, ctypes.c_int]
     lib.pycllp_b200_sparse_info.argtypes = [_vp, _ip, ctypes.POINTER(ctypes.c_longlong),
                                             ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_longlong),
                                             _dp]
@@ -217,6 +219,12 @@ class Engine(object):
         self._check(self._lib.pycllp_b200_setup_dense(self._h, m, n, _d(A), int(max_problems)),
                     "pycllp_b200_setup_dense")
         self.m, self.n, self.max_problems, self.sparse = m, n, int(max_problems), False
+
+    def set_small_kernels(self, mode):
+        """0: one 512-thread block per SM always; 1 (default): small-problem kernels where they fit
+        (128-thread kernel for dense m <= 63, else two blocks per SM); 2: only the latter.
+        Takes effect at the next setup."""
+        self._check(self._lib.pycllp_b200_set_small_kernels(self._h, int(mode)), "pycllp_b200_set_small_kernels")
 
     SPARSE_FACTOR = {"auto": 0, "tiles": 1, "dense": 2}
 

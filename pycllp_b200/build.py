@@ -10,7 +10,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpycllp_b200.so")
-SOURCES = ["ipm_kernels.cu", "ipm_kernels_py.cu", "cabi.cu"]
+SOURCES = ["ipm_kernels.cu", "ipm_kernels_py.cu", "ipm_kernels_small.cu", "cabi.cu"]
+# per-unit flags: the small-problem kernels are sized for two resident blocks per SM
+UNIT_FLAGS = {"ipm_kernels_small.cu": ["-maxrregcount=64"]}
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
 NVCC_FLAGS = [
@@ -54,7 +56,7 @@ def build(force=False, verbose=False):
         obj = os.path.join(OBJDIR, src.replace(".cu", ".o"))
         objs.append(obj)
         if force or _newer(obj, _deps(src)):
-            cmd = [nvcc] + flags + extra + ["-c", "-o", obj, os.path.join(CSRC, src)]
+            cmd = [nvcc] + flags + UNIT_FLAGS.get(src, []) + extra + ["-c", "-o", obj, os.path.join(CSRC, src)]
             jobs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for cmd, proc in jobs:

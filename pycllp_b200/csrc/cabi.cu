@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <exception>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -42,6 +43,10 @@ struct pycllp_b200_engine {
   long long launches = 0;
   unsigned long long* d_prof = nullptr;   // phase counters (debug/profiling aid)
   // sparse numeric factor: 0 auto, 1 tiles of the symbolic pattern (ipm_tiles.cuh), 2 dense packed
+  int small_mode = 1;                     // 0: never use the small-problem kernels (env PB200_SMALL=0);
+                                          // 1: both; 2: only the 64-register build of the big kernel
+  int tiny_grid = 0;                      // > 0: the 128-thread kernel of ipm_small.cuh is usable (m <= 64)
+  size_t tiny_smem = 0;
   int sparse_factor_mode = 0;
   long long tile_pairs = 0;               // tile-pair updates per factorisation (tiles mode)
   double tile_fill = 0.0;                 // tiles of the block fill / tiles of the full lower triangle
@@ -271,6 +276,24 @@ int finish_setup(pycllp_b200_engine* e, int max_problems) {
   e->sc.vec_in_smem = Vs;
   int per_sm = solve_kernel_max_blocks_per_sm(e->smem_bytes, Ls, Vs);
   if (per_sm < 1) return fail(e, PYCLLP_B200_ERR_CUDA, "kernel does not fit on an SM");
+  // small dense problems: the 128-thread kernel, everything in shared memory, >= 3 blocks per SM
+  e->tiny_grid = 0;
+  if (!e->A.sparse && m <= 63 && e->small_mode == 1) {
+    const size_t ts = tiny_kernel_smem_bytes(e->A);
+    if (ts <= e->smem_optin - 64) {
+      const int nb = tiny_kernel_blocks_per_sm(ts);
+      if (nb >= 3) {
+        e->tiny_smem = ts;
+        e->tiny_grid = std::max(1, std::min(max_problems, e->num_sms * nb));
+      }
+    }
+  }
+  // small problems: two blocks per SM with the 64-register build of the kernel
+  e->sc.small = 0;
+  if (Ls && Vs && e->small_mode != 0 && max_problems > e->num_sms) {
+    const int two = small_kernel_max_blocks_per_sm(e->smem_bytes);
+    if (two >= 2) { e->sc.small = 1; per_sm = 2; }
+  }
   e->grid = std::max(1, std::min(max_problems, e->num_sms * per_sm));
   e->max_problems = max_problems;
   double* base = nullptr;
@@ -298,8 +321,12 @@ int run(pycllp_b200_engine* e, Batch& B, cudaStream_t stream) {
   // its counter reset) before the previous one, on whatever stream, has finished
   if (e->launched) CU(cudaStreamWaitEvent(stream, e->last_done, 0));
   CU(cudaMemsetAsync(e->sc.counter, 0, sizeof(int), stream));
-  int grid = std::min(e->grid, std::max(1, B.N));
-  CU(launch_solve(e->A, B, e->sc, e->p, grid, e->smem_bytes, stream));
+  if (e->tiny_grid > 0 && !B.hook && params_are_cl(e->p)) {
+    CU(launch_solve_tiny(e->A, B, e->sc, e->p, std::min(e->tiny_grid, std::max(1, B.N)), e->tiny_smem, stream));
+  } else {
+    int grid = std::min(e->grid, std::max(1, B.N));
+    CU(launch_solve(e->A, B, e->sc, e->p, grid, e->smem_bytes, stream));
+  }
   CU(cudaEventRecord(e->last_done, stream));
   e->launched = true;
   e->launches += 1;
@@ -346,6 +373,7 @@ int pycllp_b200_create(int device, pycllp_b200_engine** out) {
   e->num_sms = prop.multiProcessorCount;
   e->smem_optin = prop.sharedMemPerBlockOptin;
   default_params(e->p, false);
+  if (const char* sm = getenv("PB200_SMALL")) e->small_mode = atoi(sm);
   *out = e;
   return 0;
 }
@@ -867,14 +895,15 @@ int pycllp_b200_phase_profile(pycllp_b200_engine* e, int enable, unsigned long l
   if (!e) return PYCLLP_B200_ERR_ARG;
   if (!e->ready) return fail(e, PYCLLP_B200_ERR_STATE, "phase_profile: call setup first");
   DeviceGuard guard(e->device);
-  const size_t bytes = (size_t)e->grid * 16 * sizeof(unsigned long long);
+  const int pgrid = std::max(e->grid, e->tiny_grid);
+  const size_t bytes = (size_t)pgrid * 16 * sizeof(unsigned long long);
   if (out16) {
     for (int k = 0; k < 16; k++) out16[k] = 0;
     if (e->d_prof) {
-      std::vector<unsigned long long> h((size_t)e->grid * 16);
+      std::vector<unsigned long long> h((size_t)pgrid * 16);
       CU(cudaDeviceSynchronize());
       CU(cudaMemcpy(h.data(), e->d_prof, bytes, cudaMemcpyDeviceToHost));
-      for (int g = 0; g < e->grid; g++)
+      for (int g = 0; g < pgrid; g++)
         for (int k = 0; k < 16; k++) out16[k] += h[(size_t)g * 16 + k];
     }
   }
@@ -951,9 +980,10 @@ int pycllp_b200_info(const pycllp_b200_engine* e, int* num_sms, int* grid, int* 
                      size_t* smem_bytes, size_t* scratch_bytes, int* factor_in_smem) {
   if (!e) return PYCLLP_B200_ERR_ARG;
   if (num_sms) *num_sms = e->num_sms;
-  if (grid) *grid = e->grid;
-  if (block) *block = NT;
-  if (smem_bytes) *smem_bytes = e->smem_bytes;
+  const bool tiny = e->tiny_grid > 0 && params_are_cl(e->p);
+  if (grid) *grid = tiny ? e->tiny_grid : e->grid;
+  if (block) *block = tiny ? 128 : NT;
+  if (smem_bytes) *smem_bytes = tiny ? e->tiny_smem : e->smem_bytes;
   if (scratch_bytes) *scratch_bytes = e->sc.slot * sizeof(double) * (size_t)e->grid;
   if (factor_in_smem) *factor_in_smem = e->sc.L_in_smem;
   return 0;
@@ -1000,6 +1030,13 @@ int pycllp_b200_tile_analysis(int m, int n, const int* indptr, const int* indice
   } catch (...) {
     return PYCLLP_B200_ERR_ARG;
   }
+}
+
+int pycllp_b200_set_small_kernels(pycllp_b200_engine* e, int mode) {
+  if (!e) return PYCLLP_B200_ERR_ARG;
+  if (mode < 0 || mode > 2) return fail(e, PYCLLP_B200_ERR_ARG, "set_small_kernels: mode must be 0, 1 or 2");
+  e->small_mode = mode;
+  return 0;
 }
 
 int pycllp_b200_set_sparse_factor(pycllp_b200_engine* e, int mode) {

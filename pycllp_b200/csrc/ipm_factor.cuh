@@ -1396,13 +1396,16 @@ static __device__ __forceinline__ bool factor_ldl_ahead(int m, Work& W, double b
       const int j0 = 8 * p, nb = min(NB, m - j0), par = p & 1;
       int* th = thbuf + par * 8;
       double* blk = xtra + 80 * par;
+#ifdef PB200_NEW_CHAIN   // (measured in situ at config 3: factor 153 k cycles per step with it, 148 k without -- the other warps are the bottleneck of most panels)
       if (nb == NB && m - j0 >= 16) {                 // full panel, full block row below it
         chain_panel8<true>(m, j0, par, p > 0, W, delta, th, blk, Wp);
         continue;
       }
       if (nb == NB) {
         chain_panel8<false>(m, j0, par, p > 0, W, delta, th, blk, Wp);
-      } else {
+      } else
+#endif
+      {
         const long long tb = phase_begin(W);
         diag_block(m, j0, nb, W, delta, th, blk, blk + 64, blk + 72);
         __syncwarp();

@@ -130,8 +130,11 @@ static bool is_cl(const Params& p) {
   return !p.nan_guard && !p.mu_mode && !p.refine_mode && p.theta_floor && !p.dz_mode;
 }
 
+bool params_are_cl(const Params& p) { return is_cl(p); }
+
 cudaError_t launch_solve(const Matrix& A, const Batch& B, const Scratch& sc, const Params& p,
                          int grid, size_t smem_bytes, cudaStream_t stream) {
+  if (is_cl(p) && sc.small) return launch_solve_small(A, B, sc, p, grid, smem_bytes, stream);
   if (is_cl(p)) return launch_solve_t<true>(A, B, sc, p, grid, smem_bytes, stream);
   return launch_solve_py(A, B, sc, p, grid, smem_bytes, stream);
 }

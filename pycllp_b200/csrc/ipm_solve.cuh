@@ -109,8 +109,10 @@ static __device__ __forceinline__ void ipm_solve_one(const Matrix& A, const Batc
     // (only while the primal residual still shrinks by >= 10 % per step: on an infeasible LP it
     // stalls, y diverges and the rounding noise of A'y -- which the reference recomputes every
     // iteration -- is what eventually trips the |sigma| > 10 |sigma_0| test, primal_normal.cl:266;
-    // a carried v has a different noise and misses it: tests/test_gpu_features.py)
-    carry_v = iter + 1 < p.carry_v && normr <= 0.9 * normr0;
+    // a carried v has a different noise and misses it: tests/test_gpu_features.py).  A residual that
+    // is already below the stop tolerance is not stalling, it is done: the end game of a converging
+    // LP, where |rho| sits at rounding level, keeps the carried v.
+    carry_v = iter + 1 < p.carry_v && (normr <= 0.9 * normr0 || normr < p.eps);
     phase_end(W, 0, t0);
     if (B.trace && tid == 0 && iter < B.trace_iters) {           // :250-252 (the kernel's verbose > 1 printf)
       double* tr = B.trace + ((size_t)q * B.trace_iters + iter) * 3;
@@ -149,8 +151,10 @@ static __device__ __forceinline__ void ipm_solve_one(const Matrix& A, const Batc
   __syncthreads();
 }
 
-template <bool LS, bool VS, bool CL>
-__global__ void __launch_bounds__(NT, 1)
+// MINB: resident blocks per SM the register allocation is sized for (1: 128 registers per thread;
+// 2: 64 -- small problems whose working set lets two blocks share an SM, ipm_kernels_small.cu)
+template <bool LS, bool VS, bool CL, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
 ipm_solve_kernel(Matrix A, Batch B, Scratch sc, Params p) {
   extern __shared__ __align__(16) double smem[];
   __shared__ int s_next;
@@ -179,9 +183,9 @@ ipm_solve_kernel(Matrix A, Batch B, Scratch sc, Params p) {
 typedef void (*solve_kernel_t)(Matrix, Batch, Scratch, Params);
 template <bool CL>
 static solve_kernel_t pick_kernel(int L_in_smem, int vec_in_smem) {
-  if (L_in_smem && vec_in_smem) return ipm_solve_kernel<true, true, CL>;
-  if (vec_in_smem) return ipm_solve_kernel<false, true, CL>;
-  return ipm_solve_kernel<false, false, CL>;
+  if (L_in_smem && vec_in_smem) return ipm_solve_kernel<true, true, CL, 1>;
+  if (vec_in_smem) return ipm_solve_kernel<false, true, CL, 1>;
+  return ipm_solve_kernel<false, false, CL, 1>;
 }
 
 template <bool CL>

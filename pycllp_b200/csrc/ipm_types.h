@@ -138,6 +138,7 @@ struct Scratch {
   size_t off_dg;
   int* counter;       // work counter
   int L_in_smem, vec_in_smem;
+  int small;          // two blocks per SM: launch the 64-register build of the kernel (ipm_kernels_small.cu)
   unsigned long long* prof;   // optional [grid][8] per-phase cycle counters (null = off)
 };
 

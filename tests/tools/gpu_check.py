@@ -135,3 +135,32 @@ if "proft" in which:
             for k, v in prof.items():
                 if v:
                     print("  %-14s %10.0f cyc/step  %5.1f%%" % (k, v / steps, 100.0 * v / tot))
+
+if "time1" in which:
+    # config-1 shape in a large batch: two blocks per SM (PB200_SMALL=0 switches that off)
+    for (m, n0, dens) in [(50, 50, 0.1), (100, 100, 1.0), (24, 40, 0.5)]:
+        N = 4096
+        A, b, c = random_equality_arrays(m, n0, dens, N)
+        eng.setup_dense(A, N)
+        print(eng.info())
+        ref = o.solve_dense(A, b[:32], c[:32])
+        for rep in range(3):
+            t = time.time(); res = eng.solve_host(b, c); dt = time.time() - t
+            print("m=%d n=%d N=%d: %.4f s -> %.0f solves/s; status0 %d; iters mean %.1f" % (
+                m, m + n0, N, dt, N / dt, int((res["status"] == 0).sum()), res["iters"].mean()))
+        compare(" vs oracle (first 32)", {k: v[:32] for k, v in res.items()}, ref)
+
+if "prof1" in which:
+    N = 4096
+    A, b, c = random_equality_arrays(50, 50, 0.1, N)
+    eng.setup_dense(A, N)
+    print(eng.info())
+    eng.solve_host(b, c)
+    eng.phase_profile(True)
+    t = time.time(); res = eng.solve_host(b, c); dt = time.time() - t
+    prof = eng.phase_profile(False)
+    steps = res["iters"].sum()
+    print("cfg1 shape N=%d %.4fs (%.0f solves/s); phase cycles per Newton step (per block):" % (N, dt, N / dt))
+    for k, v in prof.items():
+        if v:
+            print("  %-14s %10.0f cyc/step" % (k, v / steps))
