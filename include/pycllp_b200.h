@@ -99,12 +99,16 @@ int pycllp_b200_setup_sparse(pycllp_b200_engine *e, int m, int n, const int *ind
                              const int *indices, const double *data, int max_problems);
 
 /* Kernels for SMALL problems (takes effect at the next setup; default 1, env PB200_SMALL overrides):
- *   1  dense problems with m <= 63 whose whole working set (A included) fits in ~56 KB of shared
- *      memory run on the 128-thread kernel of csrc/ipm_small.cuh, four or more LPs per SM -- "one
- *      warp group per problem" at the reference's own example size (examples/random_problem.py:
- *      m = 50, n = 100); other shapes whose working set is below half an SM's shared memory run the
- *      512-thread kernel two blocks per SM (its 64-register build);
- *   2  only the latter;   0  neither (one 512-thread block per SM, as for the large shapes).
+ *   1  auto.  Dense problems with m <= 63 whose whole working set (A included) fits in a third of an
+ *      SM's shared memory run on the 128-thread kernel of csrc/ipm_small.cuh, four or more LPs per
+ *      SM -- "one warp group per problem" at the reference's own example size
+ *      (examples/random_problem.py: m = 50, n = 100) -- whenever a solve has more than 1.5 LPs per
+ *      SM (with fewer, the 512-thread kernel has the shorter latency per LP and is used).  Other
+ *      shapes whose working set is below half an SM's shared memory run the 512-thread kernel two
+ *      blocks per SM (its 64-register build);
+ *   3  as 1, but the 128-thread kernel for every batch size;   4  as 3, with every panel of its
+ *      factorisation done by the sequential rule (test switch for the fallback path);
+ *   2  only the two-blocks-per-SM build;   0  neither (one 512-thread block per SM always).
  * Same algorithm, constants and results (to rounding) in every mode. */
 int pycllp_b200_set_small_kernels(pycllp_b200_engine *e, int mode);
 

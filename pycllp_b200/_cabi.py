@@ -222,7 +222,8 @@ class Engine(object):
 
     def set_small_kernels(self, mode):
         """0: one 512-thread block per SM always; 1 (default): small-problem kernels where they fit
-        (128-thread kernel for dense m <= 63, else two blocks per SM); 2: only the latter.
+        (128-thread kernel for dense m <= 63 and batches of more than 1.5 LPs per SM, else two
+        blocks per SM); 2: only the latter; 3: the 128-thread kernel for every batch size.
         Takes effect at the next setup."""
         self._check(self._lib.pycllp_b200_set_small_kernels(self._h, int(mode)), "pycllp_b200_set_small_kernels")
 

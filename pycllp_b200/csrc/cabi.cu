@@ -278,7 +278,7 @@ int finish_setup(pycllp_b200_engine* e, int max_problems) {
   if (per_sm < 1) return fail(e, PYCLLP_B200_ERR_CUDA, "kernel does not fit on an SM");
   // small dense problems: the 128-thread kernel, everything in shared memory, >= 3 blocks per SM
   e->tiny_grid = 0;
-  if (!e->A.sparse && m <= 63 && e->small_mode == 1) {
+  if (!e->A.sparse && m <= 63 && (e->small_mode == 1 || e->small_mode >= 3)) {
     const size_t ts = tiny_kernel_smem_bytes(e->A);
     if (ts <= e->smem_optin - 64) {
       const int nb = tiny_kernel_blocks_per_sm(ts);
@@ -321,8 +321,13 @@ int run(pycllp_b200_engine* e, Batch& B, cudaStream_t stream) {
   // its counter reset) before the previous one, on whatever stream, has finished
   if (e->launched) CU(cudaStreamWaitEvent(stream, e->last_done, 0));
   CU(cudaMemsetAsync(e->sc.counter, 0, sizeof(int), stream));
-  if (e->tiny_grid > 0 && !B.hook && params_are_cl(e->p)) {
-    CU(launch_solve_tiny(e->A, B, e->sc, e->p, std::min(e->tiny_grid, std::max(1, B.N)), e->tiny_smem, stream));
+  // (one LP per SM or less: the 512-thread kernel has the shorter latency per LP; the 128-thread
+  // kernel wins as soon as there are more LPs than SMs to keep busy)
+  if (e->tiny_grid > 0 && !B.hook && params_are_cl(e->p) &&
+      (e->small_mode >= 3 || B.N > e->num_sms + e->num_sms / 2)) {
+    Scratch sct = e->sc;
+    sct.small = e->small_mode == 4 ? 4 : 0;          // 4: test switch, every panel by the sequential rule
+    CU(launch_solve_tiny(e->A, B, sct, e->p, std::min(e->tiny_grid, std::max(1, B.N)), e->tiny_smem, stream));
   } else {
     int grid = std::min(e->grid, std::max(1, B.N));
     CU(launch_solve(e->A, B, e->sc, e->p, grid, e->smem_bytes, stream));
@@ -980,7 +985,8 @@ int pycllp_b200_info(const pycllp_b200_engine* e, int* num_sms, int* grid, int* 
                      size_t* smem_bytes, size_t* scratch_bytes, int* factor_in_smem) {
   if (!e) return PYCLLP_B200_ERR_ARG;
   if (num_sms) *num_sms = e->num_sms;
-  const bool tiny = e->tiny_grid > 0 && params_are_cl(e->p);
+  const bool tiny = e->tiny_grid > 0 && params_are_cl(e->p) &&
+                    (e->small_mode >= 3 || e->max_problems > e->num_sms + e->num_sms / 2);
   if (grid) *grid = tiny ? e->tiny_grid : e->grid;
   if (block) *block = tiny ? 128 : NT;
   if (smem_bytes) *smem_bytes = tiny ? e->tiny_smem : e->smem_bytes;
@@ -1034,7 +1040,7 @@ int pycllp_b200_tile_analysis(int m, int n, const int* indptr, const int* indice
 
 int pycllp_b200_set_small_kernels(pycllp_b200_engine* e, int mode) {
   if (!e) return PYCLLP_B200_ERR_ARG;
-  if (mode < 0 || mode > 2) return fail(e, PYCLLP_B200_ERR_ARG, "set_small_kernels: mode must be 0, 1 or 2");
+  if (mode < 0 || mode > 4) return fail(e, PYCLLP_B200_ERR_ARG, "set_small_kernels: mode must be 0 .. 4");
   e->small_mode = mode;
   return 0;
 }

@@ -53,7 +53,7 @@ inline size_t small_smem_doubles(int m, int n, int nd) {
   o += 6 * al(m + 1);                       // y b dy S RHS D
   o += 3 * (size_t)lda;                     // dg g1 g2
   o += al(n) + al((n + 1) / 2);             // colval, colrow (ints)
-  o += al((m + 2) / 2);                     // column offsets (ints)
+  o += 2 * al((m + 2) / 2);                 // column offsets, singleton row pointers (ints)
   return o;
 }
 
@@ -62,9 +62,10 @@ struct SmallWork {
   double *x, *z, *t, *d, *w, *c;
   double *y, *b, *dy, *S, *RHS, *D;
   double *dg, *g1, *g2, *colval;
-  int *colrow, *offs;
+  int *colrow, *offs, *sptr;     // sptr: sing_ptr (CSR by row of the singleton columns)
   int lda, T;
   unsigned long long* prof;      // optional per-block phase counters (thread 0)
+  bool exact;                    // test switch: every panel by the sequential rule (Scratch::small == 4)
 };
 
 __device__ __forceinline__ long long s_t0(const SmallWork& W) { return W.prof ? clock64() : 0; }
@@ -124,35 +125,43 @@ static __device__ __forceinline__ void s_At_times(const Matrix& A, const SmallWo
   s_bar();
 }
 
-// o1 = A u1, o2 = A u2 (one pass over the shared-memory operand; warp per row)
+// o1 = A u1, o2 = A u2 in one pass over the shared-memory operand: a row is split over the four
+// lanes of a quad (lane kq takes the columns k = kq mod 4 -- the conflict-free access pattern of
+// the DMMA fragments), eight rows per warp and round, two shuffles per sum
 static __device__ __forceinline__ void s_A_times2(const Matrix& A, const SmallWork& W, const double* u1, const double* u2,
                                                   double* o1, double* o2) {
+  const unsigned FULL = 0xffffffffu;
   const int m = A.m, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, kq = lane & 3;
   for (int k = tid; k < W.lda; k += SNT) {
     const int j = (k < A.nd) ? __ldg(A.dcols + k) : 0;
     W.g1[k] = (k < A.nd) ? u1[j] : 0.0;
     W.g2[k] = (k < A.nd) ? u2[j] : 0.0;
   }
   s_bar();
-  for (int i = warp; i < m; i += SNW) {
-    const double* a = W.As + (size_t)i * W.lda;
+  for (int i0 = 8 * warp; i0 < m; i0 += 8 * SNW) {
+    const int i = i0 + g;                                   // (rows >= m of As are zero)
+    const double* a = W.As + (size_t)i * W.lda + kq;
     double s1 = 0.0, s2 = 0.0;
-    for (int k = lane; k < W.lda; k += 32) {
+    for (int k = 0; k < W.lda; k += 4) {
       const double av = a[k];
-      s1 = fma(av, W.g1[k], s1);
-      s2 = fma(av, W.g2[k], s2);
+      s1 = fma(av, W.g1[k + kq], s1);
+      s2 = fma(av, W.g2[k + kq], s2);
     }
-    // singleton columns of this row (slacks): lanes over the row's list
-    const int p0 = __ldg(A.sing_ptr + i), p1 = __ldg(A.sing_ptr + i + 1);
-    for (int p = p0 + lane; p < p1; p += 32) {
-      const double av = __ldg(A.sing_a + p);
-      const int j = __ldg(A.sing_col + p);
-      s1 = fma(av, u1[j], s1);
-      s2 = fma(av, u2[j], s2);
+    // singleton columns of this row (slacks): the row's list split over the quad
+    if (i < m) {
+      for (int p = W.sptr[i] + kq; p < W.sptr[i + 1]; p += 4) {
+        const double av = __ldg(A.sing_a + p);
+        const int j = __ldg(A.sing_col + p);
+        s1 = fma(av, u1[j], s1);
+        s2 = fma(av, u2[j], s2);
+      }
     }
-    s1 = warp_sum(s1);
-    s2 = warp_sum(s2);
-    if (lane == 0) { o1[i] = s1; o2[i] = s2; }
+    s1 += __shfl_xor_sync(FULL, s1, 1);
+    s2 += __shfl_xor_sync(FULL, s2, 1);
+    s1 += __shfl_xor_sync(FULL, s1, 2);
+    s2 += __shfl_xor_sync(FULL, s2, 2);
+    if (kq == 0 && i < m) { o1[i] = s1; o2[i] = s2; }
   }
   s_bar();
 }
@@ -189,7 +198,7 @@ static __device__ __forceinline__ void s_form_M(const Matrix& A, const SmallWork
   s_bar();
   // singleton columns add a^2 d to the diagonal only
   for (int i = tid; i < m; i += SNT) {
-    const int p0 = __ldg(A.sing_ptr + i), p1 = __ldg(A.sing_ptr + i + 1);
+    const int p0 = W.sptr[i], p1 = W.sptr[i + 1];
     double s = 0.0;
     for (int p = p0; p < p1; p++) s = fma(__ldg(A.sing_w + p), W.d[__ldg(A.sing_col + p)], s);
     if (p1 > p0) {
@@ -213,12 +222,15 @@ __device__ __forceinline__ double warp_max_pos(double v) {
 
 // Modified LDL' in place (ldl.cl:349-376), right-looking by panels of eight columns; row m = the
 // right-hand side kept in S: on exit S = (L D)^-1 RHS.
-//   panel: one thread per row (rows j0 .. m), the row's eight entries in registers; the eight
-//          columns are eliminated one at a time by the exact sequential rule -- theta_j by two
-//          integer warp reductions (+ one 64-thread named barrier when the rows span two warps),
-//          the unscaled diagonal-block column broadcast through shared memory, double-buffered;
+//   panel: one thread per row (rows j0 .. m), the row's eight entries in registers.  Speculative
+//          pass without any communication: every lane eliminates the 8x8 diagonal block itself
+//          (D_j = max(|d_j|, delta)) and solves its own row against it; theta_j is accumulated by
+//          integer warp reductions and checked once (one 64-thread barrier.red when the rows span
+//          two warps).  Should (theta_j/beta)^2 exceed a D_j -- it cannot for a positive
+//          semi-definite M, up to rounding -- the panel is redone from memory by the sequential
+//          rule, column by column with a block-wide theta_j;
 //   trailing matrix: 8x8 tiles of the lower triangle -= L(I, panel) D L(J, panel)', two DMMAs each.
-static __device__ __forceinline__ void s_factor(int m, const SmallWork& W, double beta, double delta) {
+static __device__ __forceinline__ void s_factor(int m, const SmallWork& W, double beta, double delta, bool exact) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, tg = lane & 3;
   const int nthr = (m + 1 + 31) & ~31;             // threads that own a row (32 or 64)
@@ -229,6 +241,7 @@ static __device__ __forceinline__ void s_factor(int m, const SmallWork& W, doubl
   double* rsm = W.red + 8;                          // [2][2]
   for (int p = 0; p < np; p++) {
     const int j0 = 8 * p, nb = min(8, m - j0);
+    long long tq = s_t0(W);
     if (tid < nthr) {
       const int r = tid;
       const bool live = r >= j0 && r <= m;
@@ -239,13 +252,77 @@ static __device__ __forceinline__ void s_factor(int m, const SmallWork& W, doubl
         c[jj] = 0.0;
         if (live && jj < nb && jj <= jlim) c[jj] = (r < m) ? L[W.offs[j0 + jj] + r] : W.S[j0 + jj];
       }
+      // ---- speculative pass: no communication at all.  Every lane eliminates the 8x8 diagonal
+      // block itself (36 entries in registers, D_j = max(|d_j|, delta): the theta term of
+      // ldl.cl:368 assumed inactive, as it is for a positive semi-definite M), then solves its own
+      // row against the block; theta_j is only accumulated and checked at the end.
+      bool bad = false;
+      if (!exact) {
+        double e[8][8], rr[8];
 #pragma unroll
-      for (int jj = 0; jj < 8; jj++) {
-        if (jj < nb) {                              // (block-uniform)
+        for (int j = 0; j < 8; j++)
+#pragma unroll
+          for (int i = j; i < 8; i++)
+            e[i][j] = (i < nb) ? L[W.offs[min(j0 + j, m - 1)] + j0 + i] : (i == j ? 1.0 : 0.0);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          rr[j] = rcp_pos64(fmax(fabs(e[j][j]), delta));
+#pragma unroll
+          for (int i = j + 1; i < 8; i++) {
+            const double l = e[i][j] * rr[j];
+#pragma unroll
+            for (int k = j + 1; k <= i; k++) e[i][k] = fma(-l, e[k][j], e[i][k]);
+          }
+        }
+        const int ri = r - j0;                      // this row's index inside the panel (rhs row: > 7)
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          if (k < nb) {
+            const double Dk = fmax(fabs(e[k][k]), delta);
+            // theta_k over this warp's rows below the pivot; (theta/beta)^2 > D_k would activate the clamp
+            const double th = warp_max_pos((live && ri > k && r < m) ? fabs(c[k]) : 0.0);
+            const double q = th * inv_beta;
+            bad |= !(q * q <= Dk);
+            if (live && ri > k) {
+              const double lk = c[k] * rr[k];
+              c[k] = lk;
+#pragma unroll
+              for (int j2 = k + 1; j2 < 8; j2++)
+                if (j2 <= jlim && j2 < nb) c[j2] = fma(-lk, e[j2][k], c[j2]);
+            } else if (ri == k) {
+              c[k] = 1.0;
+              W.D[j0 + k] = Dk;
+            }
+          }
+        }
+        // any warp's partial maximum over the threshold <=> the block maximum is
+        if (nthr > 32) {
+          unsigned any;
+          asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %1, 0;\n\tbarrier.red.or.pred p, 1, 64, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                       : "=r"(any) : "r"((unsigned)bad) : "memory");
+          bad = any != 0;
+        } else {
+          bad = __any_sync(0xffffffffu, bad);
+        }
+        if (bad) {                                  // nothing has been stored yet: reload and redo exactly
+#pragma unroll
+          for (int jj = 0; jj < 8; jj++) {
+            c[jj] = 0.0;
+            if (live && jj < nb && jj <= jlim) c[jj] = (r < m) ? L[W.offs[j0 + jj] + r] : W.S[j0 + jj];
+          }
+        }
+      }
+      if (exact || bad) {
+        // ---- the sequential rule, one column at a time with a block-wide theta ----
+#pragma unroll 1
+        for (int jj = 0; jj < nb; jj++) {
           double* wb = wsm + 8 * (jj & 1);
           double* rb = rsm + 2 * (jj & 1);
-          if (r >= j0 && r < j0 + 8) wb[r - j0] = c[jj];      // unscaled c_{r j} of the diagonal block
-          double th = (live && r > j0 + jj && r < m) ? fabs(c[jj]) : 0.0;
+          double cj = c[0];
+#pragma unroll
+          for (int q2 = 1; q2 < 8; q2++) cj = (jj == q2) ? c[q2] : cj;
+          if (r >= j0 && r < j0 + 8) wb[r - j0] = cj;      // unscaled c_{r j} of the diagonal block
+          double th = (live && r > j0 + jj && r < m) ? fabs(cj) : 0.0;
           th = warp_max_pos(th);
           if (nthr > 32) {
             if (lane == 0) rb[warp] = th;
@@ -257,13 +334,16 @@ static __device__ __forceinline__ void s_factor(int m, const SmallWork& W, doubl
           const double q = th * inv_beta;
           const double Dj = fmax(fabs(wb[jj]), fmax(q * q, delta));   // ldl.cl:368
           if (live && r > j0 + jj) {
-            const double l = c[jj] / Dj;             // (a true division, like ldl.cl:373: the statuses of
-            c[jj] = l;                               //  diverging infeasible LPs feel the last bit)
+            const double l = cj / Dj;
 #pragma unroll
-            for (int j2 = jj + 1; j2 < 8; j2++)
-              if (j2 <= jlim && j2 < nb) c[j2] = fma(-l, wb[j2], c[j2]);
+            for (int j2 = 0; j2 < 8; j2++) {
+              if (j2 == jj) c[j2] = l;
+              else if (j2 > jj && j2 <= jlim && j2 < nb) c[j2] = fma(-l, wb[j2], c[j2]);
+            }
           } else if (r == j0 + jj) {
-            c[jj] = 1.0;
+#pragma unroll
+            for (int j2 = 0; j2 < 8; j2++)
+              if (j2 == jj) c[j2] = 1.0;
             W.D[j0 + jj] = Dj;
           }
         }
@@ -278,6 +358,8 @@ static __device__ __forceinline__ void s_factor(int m, const SmallWork& W, doubl
       }
     }
     s_bar();
+    s_t1(W, 9, tq);                                 // (profile slots: f_diag = panels, f_old = trailing updates)
+    tq = s_t0(W);
     if (j0 + 8 < m) {
       const int Tt = W.T - p - 1, ntile = Tt * (Tt + 1) / 2;
       const int oa1 = W.offs[j0 + tg], oa2 = W.offs[j0 + 4 + tg];
@@ -306,6 +388,7 @@ static __device__ __forceinline__ void s_factor(int m, const SmallWork& W, doubl
       }
       s_bar();
     }
+    s_t1(W, 13, tq);
   }
 }
 
@@ -369,7 +452,7 @@ static __device__ __forceinline__ void s_solve_normal(const Matrix& A, const Sma
     W.S[i] = W.RHS[i];
   }
   const double beta = sqrt(s_block_max(bmax, W.red));
-  s_factor(m, W, beta, p.ldl_delta);
+  s_factor(m, W, beta, p.ldl_delta, W.exact);
   s_t1(W, 2, t0);
   t0 = s_t0(W);
   if (tid < 32) s_back_warp(m, W);
@@ -509,14 +592,16 @@ ipm_small_kernel(Matrix A, Batch B, Scratch sc, Params p) {
   W.colval = smem + o; o += al(n);
   W.colrow = reinterpret_cast<int*>(smem + o); o += al((n + 1) / 2);
   W.offs = reinterpret_cast<int*>(smem + o); o += al((m + 2) / 2);
+  W.sptr = reinterpret_cast<int*>(smem + o); o += al((m + 2) / 2);
   W.prof = sc.prof ? sc.prof + (size_t)blockIdx.x * 16 : nullptr;
+  W.exact = sc.small == 4;
   // the shared matrix, once per block
   for (int e = tid; e < 8 * W.T * W.lda; e += SNT) {
     const int i = e / W.lda, k = e - i * W.lda;
     W.As[e] = (i < m && k < A.nd) ? A.Ad[(size_t)i * A.ldd + k] : 0.0;
   }
   for (int j = tid; j < n; j += SNT) { W.colrow[j] = A.colrow[j]; W.colval[j] = A.colval[j]; }
-  for (int j = tid; j <= m; j += SNT) W.offs[j] = (j < m) ? packed_off(j, m) : 0;
+  for (int j = tid; j <= m; j += SNT) { W.offs[j] = (j < m) ? packed_off(j, m) : 0; W.sptr[j] = A.sing_ptr[j]; }
   for (size_t e = tid; e < packed_doubles(m); e += SNT) { W.L[e] = 0.0; W.Mp[e] = 0.0; }
   s_bar();
   for (;;) {

@@ -164,3 +164,19 @@ if "prof1" in which:
     for k, v in prof.items():
         if v:
             print("  %-14s %10.0f cyc/step" % (k, v / steps))
+
+if "prof1s" in which:
+    # one LP per block, alone on its SM: latency of each phase of the 128-thread kernel
+    N = 64
+    A, b, c = random_equality_arrays(50, 50, 0.1, N)
+    eng.setup_dense(A, N)
+    print(eng.info())
+    eng.solve_host(b, c)
+    eng.phase_profile(True)
+    t = time.time(); res = eng.solve_host(b, c); dt = time.time() - t
+    prof = eng.phase_profile(False)
+    steps = res["iters"].sum()
+    print("cfg1 N=%d %.4fs; phase cycles per Newton step (one block per SM):" % (N, dt))
+    for k, v in prof.items():
+        if v:
+            print("  %-14s %10.0f cyc/step" % (k, v / steps))
