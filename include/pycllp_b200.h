@@ -122,6 +122,17 @@ int pycllp_b200_set_small_kernels(pycllp_b200_engine *e, int mode);
  * The tiles mode keeps no copy of M and therefore has no iterative refinement (max_refine must
  * be 0, which is the sparse default and what the reference's sparse path does, ldl.cl:698-711). */
 int pycllp_b200_set_sparse_factor(pycllp_b200_engine *e, int mode);
+/* Ordering of the constraints for the tile-sparse factor (takes effect at the next setup_sparse):
+ *   0  auto (default): reverse Cuthill-McKee on the graph of A A' when that gives fewer tiles than
+ *      the order the constraints come in;   1  natural order always (what the reference does,
+ *      cl.py:185-196);   2  RCM whenever the tile factor is used.
+ * A symmetric reordering of the constraints leaves the LP and its iterates unchanged up to rounding;
+ * b is read and y written through the permutation, callers never see it.
+ * pycllp_b200_sparse_reordered: 1 if the current engine solves with reordered constraints. */
+int pycllp_b200_set_sparse_ordering(pycllp_b200_engine *e, int mode);
+/* Host-only: that RCM ordering for the CSR pattern of A; perm[i] = the caller's row at position i. */
+int pycllp_b200_rcm_ordering(int m, int n, const int *indptr, const int *indices, int *perm);
+int pycllp_b200_sparse_reordered(const pycllp_b200_engine *e);
 /* After setup_sparse: which factor is in use, its doubles per LP vs the dense m(m+1)/2, the tile
  * pair updates per factorisation and the block fill fraction. Any pointer may be NULL. */
 int pycllp_b200_sparse_info(const pycllp_b200_engine *e, int *tiles_mode, long long *factor_doubles,

@@ -28,7 +28,8 @@ EXPORTS = (
     "pycllp_b200_host_free", "pycllp_b200_host_register", "pycllp_b200_host_unregister",
     "pycllp_b200_solve_device_packed", "pycllp_b200_fp64_probe", "pycllp_b200_set_sparse_factor",
     "pycllp_b200_sparse_info", "pycllp_b200_tile_analysis", "pycllp_b200_sparse_ldl",
-    "pycllp_b200_set_small_kernels",
+    "pycllp_b200_set_small_kernels", "pycllp_b200_set_sparse_ordering", "pycllp_b200_sparse_reordered",
+    "pycllp_b200_rcm_ordering",
 )
 
 
@@ -91,6 +92,9 @@ def load_library():
                                            ctypes.c_double, ctypes.c_double]
     lib.pycllp_b200_set_sparse_factor.argtypes = [_vp, ctypes.c_int]
     lib.pycllp_b200_set_small_kernels.argtypes = [_vp, ctypes.c_int]
+    lib.pycllp_b200_set_sparse_ordering.argtypes = [_vp, ctypes.c_int]
+    lib.pycllp_b200_sparse_reordered.argtypes = [_vp]
+    lib.pycllp_b200_rcm_ordering.argtypes = [ctypes.c_int, ctypes.c_int, _ip, _ip, _ip]
     lib.pycllp_b200_sparse_info.argtypes = [_vp, _ip, ctypes.POINTER(ctypes.c_longlong),
                                             ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_longlong),
                                             _dp]
@@ -108,6 +112,21 @@ def _i(a):
 
 def _f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def rcm_ordering(csr):
+    """Host-only: the band-reducing ordering of the constraints ``setup_sparse`` considers for the
+    tile-sparse factor; ``perm[i]`` = the row of ``csr`` placed at position i."""
+    lib = load_library()
+    csr = csr.tocsr()
+    m, n = csr.shape
+    indptr = np.ascontiguousarray(csr.indptr, dtype=np.int32)
+    indices = np.ascontiguousarray(csr.indices, dtype=np.int32)
+    perm = np.zeros(m, np.int32)
+    rc = lib.pycllp_b200_rcm_ordering(m, n, _i(indptr), _i(indices), _i(perm))
+    if rc != 0:
+        raise RuntimeError("pycllp_b200_rcm_ordering failed (%d)" % rc)
+    return perm
 
 
 def tile_analysis(csr):
@@ -229,12 +248,18 @@ class Engine(object):
 
     SPARSE_FACTOR = {"auto": 0, "tiles": 1, "dense": 2}
 
-    def setup_sparse(self, csr, max_problems, factor="auto"):
+    SPARSE_ORDERING = {"auto": 0, "natural": 1, "rcm": 2}
+
+    def setup_sparse(self, csr, max_problems, factor="auto", ordering="auto"):
         """``csr``: scipy.sparse CSR matrix (sorted indices).  ``factor``: numeric factor of the
         sparse path -- 'tiles' (L on its symbolic fill pattern, 8x8 tiles, memory ~ nnz(L)),
-        'dense' (packed dense kernels) or 'auto'."""
+        'dense' (packed dense kernels) or 'auto'.  ``ordering`` (tiles only): 'natural' (the order
+        the constraints come in, as the reference), 'rcm' (band-reducing reordering of the
+        constraints) or 'auto' (RCM when it gives fewer tiles)."""
         self._check(self._lib.pycllp_b200_set_sparse_factor(self._h, self.SPARSE_FACTOR[factor]),
                     "pycllp_b200_set_sparse_factor")
+        self._check(self._lib.pycllp_b200_set_sparse_ordering(self._h, self.SPARSE_ORDERING[ordering]),
+                    "pycllp_b200_set_sparse_ordering")
         csr = csr.tocsr()
         csr.sort_indices()
         m, n = csr.shape
@@ -254,7 +279,9 @@ class Engine(object):
         self._check(self._lib.pycllp_b200_sparse_info(self._h, ctypes.byref(mode), ctypes.byref(fd),
                                                       ctypes.byref(dd), ctypes.byref(up), ctypes.byref(fill)),
                     "pycllp_b200_sparse_info")
-        return {"factor": "tiles" if mode.value else "dense", "factor_doubles": fd.value,
+        return {"factor": "tiles" if mode.value else "dense",
+                "ordering": "rcm" if self._lib.pycllp_b200_sparse_reordered(self._h) else "natural",
+                "factor_doubles": fd.value,
                 "dense_factor_doubles": dd.value, "update_pairs": up.value, "tile_fill": fill.value}
 
     def get_params(self):

@@ -47,6 +47,7 @@ struct pycllp_b200_engine {
                                           // 1: both; 2: only the 64-register build of the big kernel
   int tiny_grid = 0;                      // > 0: the 128-thread kernel of ipm_small.cuh is usable (m <= 64)
   size_t tiny_smem = 0;
+  int sparse_order_mode = 0;              // 0 auto (RCM when it gives fewer tiles), 1 natural order, 2 RCM
   int sparse_factor_mode = 0;
   long long tile_pairs = 0;               // tile-pair updates per factorisation (tiles mode)
   double tile_fill = 0.0;                 // tiles of the block fill / tiles of the full lower triangle
@@ -155,6 +156,63 @@ void free_matrix(pycllp_b200_engine* e) {
   e->ready = false;
 }
 
+
+// Reverse Cuthill-McKee ordering of the graph of A A' (lower pattern me_i > me_j): perm[i] = the
+// original row placed at position i.  A band-reducing ordering keeps the 8x8 tiles of the block
+// fill dense, which is what the tile-sparse factor needs (a minimum-degree ordering reduces the
+// scalar fill but scatters it over many nearly empty tiles).  The reference factorises in the
+// order the constraints come in (cl.py:185-196); a symmetric reordering of the constraints leaves
+// the LP and its interior-point iterates unchanged up to rounding.
+static std::vector<int> rcm_ordering(int m, const std::vector<int>& me_i, const std::vector<int>& me_j) {
+  std::vector<int> deg(m, 0), ptr(m + 1, 0);
+  for (size_t e = 0; e < me_i.size(); e++)
+    if (me_i[e] != me_j[e]) { deg[me_i[e]]++; deg[me_j[e]]++; }
+  for (int i = 0; i < m; i++) ptr[i + 1] = ptr[i] + deg[i];
+  std::vector<int> adj(ptr[m]), fill(ptr.begin(), ptr.end() - 1);
+  for (size_t e = 0; e < me_i.size(); e++)
+    if (me_i[e] != me_j[e]) { adj[fill[me_i[e]]++] = me_j[e]; adj[fill[me_j[e]]++] = me_i[e]; }
+  for (int i = 0; i < m; i++)
+    std::sort(adj.begin() + ptr[i], adj.begin() + ptr[i + 1], [&](int a, int b) { return deg[a] != deg[b] ? deg[a] < deg[b] : a < b; });
+  std::vector<int> order, level(m, -1);
+  order.reserve(m);
+  std::vector<char> seen(m, 0);
+  std::vector<int> byDeg(m);
+  for (int i = 0; i < m; i++) byDeg[i] = i;
+  std::stable_sort(byDeg.begin(), byDeg.end(), [&](int a, int b) { return deg[a] < deg[b]; });
+  auto bfs = [&](int root, std::vector<int>& out) {      // level structure from root; returns its last node
+    out.clear();
+    out.push_back(root);
+    level[root] = 0;
+    for (size_t h = 0; h < out.size(); h++) {
+      const int v = out[h];
+      for (int q = ptr[v]; q < ptr[v + 1]; q++)
+        if (level[adj[q]] < 0 && !seen[adj[q]]) { level[adj[q]] = level[v] + 1; out.push_back(adj[q]); }
+    }
+    const int last = out.back();
+    return last;
+  };
+  std::vector<int> comp;
+  for (int s0 : byDeg) {
+    if (seen[s0]) continue;
+    // pseudo-peripheral start: repeat the BFS from the (lowest-degree) node of the last level while it deepens
+    int root = s0, depth = -1;
+    for (int it = 0; it < 8; it++) {
+      const int last = bfs(root, comp);
+      const int d = level[last];
+      int cand = last;
+      for (int v : comp)
+        if (level[v] == d && deg[v] < deg[cand]) cand = v;
+      for (int v : comp) level[v] = -1;
+      if (d <= depth) break;
+      depth = d;
+      root = cand;
+    }
+    bfs(root, comp);
+    for (int v : comp) { seen[v] = 1; level[v] = -1; order.push_back(v); }
+  }
+  std::reverse(order.begin(), order.end());
+  return order;
+}
 
 // Symbolic analysis of the tile-sparse factor (ipm_tiles.cuh) from the lower pattern (me_i >= me_j)
 // of A A': block elimination tree and block fill at 8x8-tile granularity, natural order (the
@@ -491,12 +549,27 @@ int pycllp_b200_setup_dense(pycllp_b200_engine* e, int m, int n, const double* A
 }
 
 static int setup_sparse_impl(pycllp_b200_engine* e, int m, int n, const int* indptr,
-                             const int* indices, const double* data, int max_problems) {
+                             const int* indices, const double* data, int max_problems,
+                             const int* rperm = nullptr) {
   // indptr comes from the caller: it must be a CSR row pointer before anything is sized from it
   if (indptr[0] != 0) return fail(e, PYCLLP_B200_ERR_ARG, "setup_sparse: indptr[0] != 0");
   for (int i = 0; i < m; i++)
     if (indptr[i + 1] < indptr[i])
       return fail(e, PYCLLP_B200_ERR_ARG, "setup_sparse: indptr is not non-decreasing");
+  // rperm: analyse and solve with the constraints reordered (internal row i = the caller's row rperm[i])
+  std::vector<int> p_indptr, p_indices;
+  std::vector<double> p_data;
+  if (rperm) {
+    p_indptr.assign(m + 1, 0);
+    for (int i = 0; i < m; i++) p_indptr[i + 1] = p_indptr[i] + (indptr[rperm[i] + 1] - indptr[rperm[i]]);
+    p_indices.resize(p_indptr[m]);
+    p_data.resize(p_indptr[m]);
+    for (int i = 0; i < m; i++) {
+      std::copy(indices + indptr[rperm[i]], indices + indptr[rperm[i] + 1], p_indices.begin() + p_indptr[i]);
+      std::copy(data + indptr[rperm[i]], data + indptr[rperm[i] + 1], p_data.begin() + p_indptr[i]);
+    }
+    indptr = p_indptr.data(); indices = p_indices.data(); data = p_data.data();
+  }
   DeviceGuard guard(e->device);
   free_matrix(e);
   Matrix& M = e->A;
@@ -570,6 +643,21 @@ static int setup_sparse_impl(pycllp_b200_engine* e, int m, int n, const int* ind
     TileSym ts;
     const size_t cap = e->sparse_factor_mode == 1 ? (size_t)INT_MAX / 64 : (size_t)(0.4 * (double)full) + 1;
     const bool fits = tile_symbolic(m, me_i, me_j, cap, ts);
+    // a band-reducing reordering of the constraints (RCM) when it gives fewer tiles than the order
+    // the constraints came in (auto), or on request
+    if (!rperm && e->sparse_order_mode != 1 && (e->sparse_factor_mode == 1 || m > 512)) {
+      std::vector<int> perm = rcm_ordering(m, me_i, me_j), inv(m);
+      for (int i = 0; i < m; i++) inv[perm[i]] = i;
+      std::vector<int> qi(me_i.size()), qj(me_i.size());
+      for (size_t q = 0; q < me_i.size(); q++) {
+        const int a = inv[me_i[q]], b = inv[me_j[q]];
+        qi[q] = std::max(a, b); qj[q] = std::min(a, b);
+      }
+      TileSym tr2;
+      const bool fits2 = tile_symbolic(m, qi, qj, cap, tr2);
+      if (fits2 && (e->sparse_order_mode == 2 || !fits || tr2.ntiles < ts.ntiles))
+        return setup_sparse_impl(e, m, n, indptr, indices, data, max_problems, perm.data());
+    }
     if (!fits && e->sparse_factor_mode == 1)
       return fail(e, PYCLLP_B200_ERR_ARG, "setup_sparse: tile structure exceeds 32-bit positions");
     if (fits && (e->sparse_factor_mode == 1 || m > 512)) {
@@ -589,6 +677,10 @@ static int setup_sparse_impl(pycllp_b200_engine* e, int m, int n, const int* ind
       }
       if ((rc = upload(e, ts.me_pos, &M.me_pos))) return rc;
     }
+  }
+  if (rperm) {                                       // (the matrix below IS the reordered one)
+    std::vector<int> pv(rperm, rperm + m);
+    if ((rc = upload(e, pv, &M.rperm))) return rc;
   }
   if ((rc = upload(e, Ap, &M.Ap))) return rc;
   if ((rc = upload(e, Ai, &M.Ai))) return rc;
@@ -995,6 +1087,45 @@ int pycllp_b200_info(const pycllp_b200_engine* e, int* num_sms, int* grid, int* 
   return 0;
 }
 
+// lower pattern (i >= j, diagonal included where a row is non-empty) of A A' from the CSR pattern of A
+static bool aat_pattern(int m, int n, const int* indptr, const int* indices, std::vector<int>& me_i,
+                        std::vector<int>& me_j) {
+  if (indptr[0] != 0) return false;
+  for (int i = 0; i < m; i++)
+    if (indptr[i + 1] < indptr[i]) return false;
+  std::vector<std::vector<int>> colrows(n);
+  for (int i = 0; i < m; i++)
+    for (int k = indptr[i]; k < indptr[i + 1]; k++) {
+      if (indices[k] < 0 || indices[k] >= n) return false;
+      colrows[indices[k]].push_back(i);
+    }
+  std::vector<std::pair<int, int>> ent;
+  for (int k = 0; k < n; k++)
+    for (size_t a = 0; a < colrows[k].size(); a++)
+      for (size_t b = 0; b <= a; b++) ent.push_back({colrows[k][a], colrows[k][b]});
+  std::sort(ent.begin(), ent.end());
+  ent.erase(std::unique(ent.begin(), ent.end()), ent.end());
+  me_i.resize(ent.size());
+  me_j.resize(ent.size());
+  for (size_t e = 0; e < ent.size(); e++) { me_i[e] = ent[e].first; me_j[e] = ent[e].second; }
+  return true;
+}
+
+// Host-only: the RCM ordering setup_sparse would consider for this pattern; perm[i] = the caller's
+// row placed at position i.
+int pycllp_b200_rcm_ordering(int m, int n, const int* indptr, const int* indices, int* perm) {
+  if (m <= 0 || n <= 0 || !indptr || !indices || !perm) return PYCLLP_B200_ERR_ARG;
+  try {
+    std::vector<int> me_i, me_j;
+    if (!aat_pattern(m, n, indptr, indices, me_i, me_j)) return PYCLLP_B200_ERR_ARG;
+    std::vector<int> p = rcm_ordering(m, me_i, me_j);
+    std::copy(p.begin(), p.end(), perm);
+    return 0;
+  } catch (...) {
+    return PYCLLP_B200_ERR_ARG;
+  }
+}
+
 // Host-only: the symbolic analysis of the tile-sparse factor for a CSR pattern (no device, no
 // engine) -- what setup_sparse computes, exposed so that the CPU test-suite can check it.
 int pycllp_b200_tile_analysis(int m, int n, const int* indptr, const int* indices, int* nbk, int* ntiles,
@@ -1002,25 +1133,8 @@ int pycllp_b200_tile_analysis(int m, int n, const int* indptr, const int* indice
                               int* updb) {
   if (m <= 0 || n <= 0 || !indptr || !indices) return PYCLLP_B200_ERR_ARG;
   try {
-    if (indptr[0] != 0) return PYCLLP_B200_ERR_ARG;
-    for (int i = 0; i < m; i++)
-      if (indptr[i + 1] < indptr[i]) return PYCLLP_B200_ERR_ARG;
-    const int nnz = indptr[m];
-    std::vector<std::vector<int>> colrows(n);
-    for (int i = 0; i < m; i++)
-      for (int k = indptr[i]; k < indptr[i + 1]; k++) {
-        if (indices[k] < 0 || indices[k] >= n) return PYCLLP_B200_ERR_ARG;
-        colrows[indices[k]].push_back(i);
-      }
-    (void)nnz;
-    std::vector<std::pair<int, int>> ent;
-    for (int k = 0; k < n; k++)
-      for (size_t a = 0; a < colrows[k].size(); a++)
-        for (size_t b = 0; b <= a; b++) ent.push_back({colrows[k][a], colrows[k][b]});
-    std::sort(ent.begin(), ent.end());
-    ent.erase(std::unique(ent.begin(), ent.end()), ent.end());
-    std::vector<int> me_i(ent.size()), me_j(ent.size());
-    for (size_t e = 0; e < ent.size(); e++) { me_i[e] = ent[e].first; me_j[e] = ent[e].second; }
+    std::vector<int> me_i, me_j;
+    if (!aat_pattern(m, n, indptr, indices, me_i, me_j)) return PYCLLP_B200_ERR_ARG;
     TileSym ts;
     if (!tile_symbolic(m, me_i, me_j, (size_t)INT_MAX / 64, ts)) return PYCLLP_B200_ERR_ARG;
     if (nbk) *nbk = ts.nbk;
@@ -1051,6 +1165,15 @@ int pycllp_b200_set_sparse_factor(pycllp_b200_engine* e, int mode) {
   e->sparse_factor_mode = mode;
   return 0;
 }
+
+int pycllp_b200_set_sparse_ordering(pycllp_b200_engine* e, int mode) {
+  if (!e) return PYCLLP_B200_ERR_ARG;
+  if (mode < 0 || mode > 2) return fail(e, PYCLLP_B200_ERR_ARG, "set_sparse_ordering: mode must be 0 (auto), 1 (natural) or 2 (rcm)");
+  e->sparse_order_mode = mode;
+  return 0;
+}
+
+int pycllp_b200_sparse_reordered(const pycllp_b200_engine* e) { return (e && e->ready && e->A.rperm) ? 1 : 0; }
 
 int pycllp_b200_sparse_info(const pycllp_b200_engine* e, int* tiles_mode, long long* factor_doubles,
                             long long* dense_factor_doubles, long long* update_pairs, double* tile_fill) {

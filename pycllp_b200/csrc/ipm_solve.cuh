@@ -70,8 +70,9 @@ static __device__ __forceinline__ void ipm_solve_one(const Matrix& A, const Batc
     W.z[j] = z0;
   }
   for (int i = tid; i < m; i += NT) {
-    W.b[i] = B.b[(size_t)q * m + i];
-    W.y[i] = given ? B.y0[(size_t)q * ld0m + i] : 1.0;
+    const int io = A.rperm ? A.rperm[i] : i;        // the caller's row (constraints reordered at setup)
+    W.b[i] = B.b[(size_t)q * m + io];
+    W.y[i] = given ? B.y0[(size_t)q * ld0m + io] : 1.0;
   }
   __syncthreads();
 
@@ -79,7 +80,7 @@ static __device__ __forceinline__ void ipm_solve_one(const Matrix& A, const Batc
     double nr, ns;
     prepare_rhs<VS>(A, W, B.mu, nr, ns);
     solve_normal<LS, VS, CL>(A, W, p);
-    for (int i = tid; i < m; i += NT) B.dy_out[(size_t)q * m + i] = W.dy[i];
+    for (int i = tid; i < m; i += NT) B.dy_out[(size_t)q * m + (A.rperm ? A.rperm[i] : i)] = W.dy[i];
     __syncthreads();
     return;
   }
@@ -143,7 +144,7 @@ static __device__ __forceinline__ void ipm_solve_one(const Matrix& A, const Batc
   const int lds = B.ld_s ? B.ld_s : 1;
   if (B.x) for (int j = tid; j < n; j += NT) B.x[(size_t)q * ldx + j] = W.x[j];
   if (B.z) for (int j = tid; j < n; j += NT) B.z[(size_t)q * ldz + j] = W.z[j];
-  if (B.y) for (int i = tid; i < m; i += NT) B.y[(size_t)q * ldy + i] = W.y[i];
+  if (B.y) for (int i = tid; i < m; i += NT) B.y[(size_t)q * ldy + (A.rperm ? A.rperm[i] : i)] = W.y[i];
   if (tid == 0) {
     if (B.status) B.status[(size_t)q * lds] = stat;
     if (B.iters) B.iters[(size_t)q * lds] = iter;

@@ -70,6 +70,9 @@ struct Matrix {
   // 64 t + 8 c + r.  Target tile t receives  - L(tl_upda[p]) D L(tl_updb[p])'  for
   // p in [tl_updptr[t], tl_updptr[t+1]).  me_pos[e]: where entry e of the pattern of A A' goes.
   int tiles, nbk, ntiles;
+  // optional symmetric reordering of the constraints (rows of A) chosen at setup to reduce the fill of
+  // L: internal row i is the caller's row rperm[i] (b is read, y written through it); null = identity
+  const int* rperm;
   const int *tl_colptr, *tl_row, *tl_col, *tl_updptr, *tl_upda, *tl_updb, *tl_updk, *me_pos;   // tl_updk[p]: block column K of pair p
 };
 

@@ -60,11 +60,13 @@ def pack_records(res, m, n):
     return rec
 
 
-def unpack_records(rec, m, n):
-    """(N, 2n+m+1) float64 records -> dict(x, y, z, status, iters) (copies)."""
+def unpack_records(rec, m, n, copy=True):
+    """(N, 2n+m+1) float64 records -> dict(x, y, z, status, iters).  ``copy=False``: x, y, z are
+    strided VIEWS of ``rec`` (no second pass over 2n+m doubles per problem on the host)."""
     rec = np.ascontiguousarray(rec)
     tail = rec[:, 2 * n + m:].view(np.int32)
-    return dict(x=rec[:, :n].copy(), y=rec[:, n:n + m].copy(), z=rec[:, n + m:2 * n + m].copy(),
+    cp = (lambda a: a.copy()) if copy else (lambda a: a)
+    return dict(x=cp(rec[:, :n]), y=cp(rec[:, n:n + m]), z=cp(rec[:, n + m:2 * n + m]),
                 status=tail[:, 0].copy(), iters=tail[:, 1].copy())
 
 

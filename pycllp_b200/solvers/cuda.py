@@ -64,6 +64,7 @@ class _CudaPrimalNormalBase(BaseSolver):
         self._preset = params.pop("preset", self._preset)
         # sparse path only: 'auto' | 'tiles' (L on its symbolic fill pattern) | 'dense'
         self._factor = params.pop("factor", "auto")
+        self._ordering = params.pop("ordering", "auto")
         self._params = params
         self._span = None
         self._out = None
@@ -78,7 +79,7 @@ class _CudaPrimalNormalBase(BaseSolver):
         self._span = (lo, hi, world, rank)
         nlocal = max(hi - lo, 1)
         if self._sparse:
-            self.engine.setup_sparse(lp.A.tocsr(), nlocal, factor=self._factor)
+            self.engine.setup_sparse(lp.A.tocsr(), nlocal, factor=self._factor, ordering=self._ordering)
         else:
             self.engine.setup_dense(np.asarray(lp.A.todense(), dtype=DTYPE), nlocal)
         if self._preset != "cl":
@@ -162,7 +163,13 @@ class _CudaPrimalNormalBase(BaseSolver):
                 self.engine.solve_device_packed(nloc, b.data_ptr(), c.data_ptr(), rec.data_ptr(),
                                                 stream.cuda_stream, warm_start=warm_start)
         full = sharding.allgather_records(rec[:nloc], N, self.group)
-        return sharding.unpack_records(full.cpu().numpy(), m, n)
+        # one DMA into page-locked memory; x, y, z are handed out as views of that block
+        if st.get("host") is None or st["host"].shape != tuple(full.shape):
+            st["host"] = self.engine.pinned_empty(tuple(full.shape))
+            st["host_t"] = torch.from_numpy(st["host"])
+        st["host_t"].copy_(full, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return sharding.unpack_records(st["host"], m, n, copy=False)
 
 
 class CudaDensePrimalNormalSolver(_CudaPrimalNormalBase):

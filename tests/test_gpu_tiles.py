@@ -130,3 +130,33 @@ def test_sparse_ldl_hook_vs_dense_modified_ldl(engine, oracle):
         rows = np.repeat(np.arange(m), np.diff(pat.indptr))
         np.testing.assert_allclose(Ds, D, rtol=1e-10)
         np.testing.assert_allclose(Ls, Ld[:, rows, pat.indices], rtol=1e-9, atol=1e-12)
+
+
+def test_tiles_with_reordered_constraints_vs_oracle(engine, oracle):
+    """The same staircase LP with its constraints SHUFFLED: in the order given the factor is dense;
+    setup_sparse reorders the constraints (RCM) for the tile factor, b is read and y written through
+    the permutation, and the caller sees the solution of the LP as posed -- equal to the oracle's
+    (which factorises in the given order) in status, step count and x, y, z."""
+    A0, b0, c = staircase_equality_arrays(640, 960, 24, 3, 5, seed=7)
+    rng = np.random.RandomState(1)
+    sh = rng.permutation(A0.shape[0])
+    A, b = A0.tocsr()[sh], b0[:, sh]
+    engine.setup_sparse(A, b.shape[0], factor="tiles", ordering="natural")
+    nat = engine.sparse_info()
+    engine.setup_sparse(A, b.shape[0])                       # auto: m > 512, RCM gives fewer tiles
+    si = engine.sparse_info()
+    assert si["factor"] == "tiles" and si["ordering"] == "rcm"
+    assert si["factor_doubles"] < 0.25 * nat["factor_doubles"]
+    res = engine.solve_host(b, c)
+    ref = oracle.solve_sparse(A.toarray(), b, c)
+    assert_parity(res, ref, c, "shuffled staircase, RCM")
+    assert np.abs(res["iters"] - ref.iters).max() <= 1
+    # warm start: y0 comes back through the permutation
+    r2 = engine.solve_host(b, c, warm_start=True)
+    assert (r2["status"] == 0).all() and r2["iters"].max() <= res["iters"].max()
+    # the hook goes through the permutation as well (y, b in; dy out)
+    N, (m, n) = b.shape[0], A.shape
+    x, z, y = 0.1 + rng.rand(N, n), 0.1 + rng.rand(N, n), rng.rand(N, m)
+    dy = engine.solve_primal_normal(x, z, y, b, c, 0.2)
+    dref = oracle.sparse_solve_primal_normal(A.toarray(), x, z, y, b, c, 0.2)
+    np.testing.assert_allclose(dy, dref, rtol=1e-8, atol=1e-9 * np.abs(dref).max())
