@@ -345,6 +345,25 @@ def main():
     from scipy.sparse import csr_matrix
     b_all = np.concatenate([make_problem(args.workload, r, batch=N)[1] for r in range(world)]) if world > 1 else run.b
     c_all = np.concatenate([make_problem(args.workload, r, batch=N)[2] for r in range(world)]) if world > 1 else run.c
+    # the container path a pycllp user takes: StandardLP(A0, b, c0) -> to_equality_form()
+    # -> A.tocsr() hand-off to the solver; timed on rank 0, outside the solve timing
+    containers = None
+    if rank == 0:
+        from pycllp_b200.lp import StandardLP, SparseMatrix
+        from scipy.sparse import coo_matrix
+        n0 = w["n0"]
+        t0 = time.perf_counter()
+        A0 = csr_matrix(run.A)[:, :n0].tocoo()
+        std = StandardLP(SparseMatrix(matrix=A0), run.b, run.c[:, :n0], np.zeros(N))
+        t1 = time.perf_counter()
+        eq = std.to_equality_form()
+        t2 = time.perf_counter()
+        Acsr = eq.A.tocsr()
+        t3 = time.perf_counter()
+        assert eq.ncols == n and eq.nrows == m and Acsr.nnz == csr_matrix(run.A).nnz
+        containers = {"build_StandardLP_s": t1 - t0, "to_equality_form_s": t2 - t1, "tocsr_s": t3 - t2,
+                      "problems": N, "nnz": int(Acsr.nnz)}
+        del std, eq, Acsr, A0
     lp = EqualityLP(csr_matrix(run.A), b_all, c_all, np.zeros(world * N))
     solver = solver_registry["cl_sparse_primal_normal" if run.sparse else "cl_dense_primal_normal"](
         local, group=True if world > 1 else None)
@@ -443,7 +462,7 @@ def main():
                        "exchange": ("one all_gather_into_tensor of %d B records per LP inside the timed step"
                                     % (run.width * 8)) if world > 1 else "none (1 rank)",
                        "gather_bytes_per_rank": (world * N * run.width * 8) if world > 1 else 0,
-                       "setup_s": run.setup_s,
+                       "setup_s": run.setup_s, "lp_containers": containers,
                        **({"sparse_factor": run.tile_info} if run.tile_info else {})},
             "clocks": clocks,
             "e2e": {"value": world * N * args.steps / e2e_s, "unit": "solves/s",
