@@ -326,8 +326,28 @@ static __device__ __forceinline__ void tiles_backward(const Matrix& A, Work& W, 
   __syncthreads();
 }
 
-// factor + solve on the tile pattern (sparse_solve_primal_normal, ldl.cl:655-712: no refinement)
-static __device__ __noinline__ void solve_normal_tiles(const Matrix& A, Work& W, const Params& p) {
+// factor + solve on the tile pattern (sparse_solve_primal_normal, ldl.cl:655-712: no refinement).
+// Out of line, and its arguments BY VALUE: a reference to the caller's Matrix / Work would force
+// those structs into local memory for the whole kernel (measured: the stack frame of the
+// LS = false kernels grew from 672 to 1160 bytes and configs 4 and 5 lost 6-8 %).
+struct TilesArgs {
+  int m, nme, nbk, ntiles;
+  const int *me_ptr, *me_pos, *mt_k, *tl_colptr, *tl_row, *tl_updptr, *tl_upda, *tl_updb, *tl_updk;
+  const double* mt_w;
+  double *L, *D, *S, *RHS, *dy, *d, *fb, *red;
+  unsigned long long* prof;
+  double ldl_delta;
+};
+
+static __device__ __noinline__ void solve_normal_tiles_call(TilesArgs a) {
+  Matrix A;
+  A.m = a.m; A.nme = a.nme; A.nbk = a.nbk; A.ntiles = a.ntiles;
+  A.me_ptr = a.me_ptr; A.me_pos = a.me_pos; A.mt_k = a.mt_k; A.mt_w = a.mt_w;
+  A.tl_colptr = a.tl_colptr; A.tl_row = a.tl_row; A.tl_updptr = a.tl_updptr;
+  A.tl_upda = a.tl_upda; A.tl_updb = a.tl_updb; A.tl_updk = a.tl_updk;
+  Work W;
+  W.L = a.L; W.D = a.D; W.S = a.S; W.RHS = a.RHS; W.dy = a.dy; W.d = a.d; W.fb = a.fb; W.red = a.red;
+  W.prof = a.prof;
   const int m = A.m, tid = threadIdx.x;
   long long t0 = phase_begin(W);
   tiles_form_M(A, W);
@@ -336,12 +356,24 @@ static __device__ __noinline__ void solve_normal_tiles(const Matrix& A, Work& W,
   phase_end(W, 1, t0);
   t0 = phase_begin(W);
   const double beta = sqrt(tiles_diag_absmax(A, W));
-  tiles_factor(A, W, beta, p.ldl_delta);
+  tiles_factor(A, W, beta, a.ldl_delta);
   phase_end(W, 2, t0);
   t0 = phase_begin(W);
   tiles_forward(A, W, W.RHS);
   tiles_backward(A, W);
   phase_end(W, 3, t0);
+}
+
+static __device__ __forceinline__ void solve_normal_tiles(const Matrix& A, Work& W, const Params& p) {
+  TilesArgs a;
+  a.m = A.m; a.nme = A.nme; a.nbk = A.nbk; a.ntiles = A.ntiles;
+  a.me_ptr = A.me_ptr; a.me_pos = A.me_pos; a.mt_k = A.mt_k; a.mt_w = A.mt_w;
+  a.tl_colptr = A.tl_colptr; a.tl_row = A.tl_row; a.tl_updptr = A.tl_updptr;
+  a.tl_upda = A.tl_upda; a.tl_updb = A.tl_updb; a.tl_updk = A.tl_updk;
+  a.L = W.L; a.D = W.D; a.S = W.S; a.RHS = W.RHS; a.dy = W.dy; a.d = W.d; a.fb = W.fb; a.red = W.red;
+  a.prof = W.prof;
+  a.ldl_delta = p.ldl_delta;
+  solve_normal_tiles_call(a);
 }
 
 }  // namespace pb200
