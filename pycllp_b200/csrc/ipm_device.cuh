@@ -314,6 +314,39 @@ __device__ __forceinline__ void A_times2(const Matrix& A, const double* __restri
   __syncthreads();
 }
 
+// o = A u (dense operator only), one pass over A: eight rows per warp, one 9-shuffle reduction.
+// g: scratch of ldd doubles (u gathered onto the packed columns).  Ends with __syncthreads().
+__device__ __forceinline__ void A_times1(const Matrix& A, const double* __restrict__ u, double* __restrict__ o,
+                                         double* __restrict__ g) {
+  const int m = A.m, ldd = A.ldd;
+  const int lane = threadIdx.x & 31, warp = warp_id();
+  for (int k = threadIdx.x; k < ldd; k += NT) g[k] = (k < A.nd) ? u[A.dcols[k]] : 0.0;
+  for (int i = threadIdx.x; i < m; i += NT) {
+    double s = 0.0;
+    for (int e = A.sing_ptr[i]; e < A.sing_ptr[i + 1]; e++) s += A.sing_a[e] * u[A.sing_col[e]];
+    o[i] = s;
+  }
+  __syncthreads();
+  const int q = (lane >> 2) & 7;
+  for (int i0 = warp * 8; i0 < m; i0 += NWARP * 8) {
+    const double* __restrict__ r[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) r[c] = A.Ad + (size_t)min(i0 + c, m - 1) * ldd;
+    double a[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) a[c] = 0.0;
+#pragma unroll 2
+    for (int k = lane; k < ldd; k += 32) {
+      const double v = g[k];
+#pragma unroll
+      for (int c = 0; c < 8; c++) a[c] += __ldcg(r[c] + k) * v;
+    }
+    const double t = warp_sum8(a, lane);
+    if ((lane & 3) == 0 && i0 + q < m) o[i0 + q] += t;
+  }
+  __syncthreads();
+}
+
 // ---------------------------------------------------------------------------------------
 // M = A diag(d) A'  (full symmetric m x m into W.M), returns nothing; caller syncs.
 // ---------------------------------------------------------------------------------------
@@ -530,22 +563,47 @@ static __device__ __forceinline__ double residual_M(int m, Work& W, bool signed_
   return block_max(mx, W.red);
 }
 
+// The same residual WITHOUT M:  S = RHS - A ((x/z) o (A' dy)),  M = A diag(x/z) A'.  Two passes over
+// the L2-resident operand instead of writing M (m^2 doubles per Newton step into the block's
+// scratch slot, whose dirty lines L2 keeps spilling to DRAM) and reading it back; and it leaves
+// w = A' dy in W.w, which is exactly what the step needs next -- so the step's own pass over A
+// goes away whenever the residual was computed for the final dy.  Dense operator, VS only.
+static __device__ __forceinline__ double residual_free(const Matrix& A, Work& W, bool signed_max = false) {
+  const int m = A.m, n = A.n, tid = threadIdx.x;
+  At_times(A, W.dy, W.w);
+  for (int j = tid; j < n; j += NT) W.d[j] = W.x[j] * W.w[j] / W.z[j];      // (d = x/z has done its duty in the SYRK)
+  __syncthreads();
+  A_times1(A, W.d, W.S, W.P);               // (gather buffer: the panel / stage area is idle; g1 aliases L here)
+  double mx = 0.0;
+  for (int i = tid; i < m; i += NT) {
+    const double res = W.RHS[i] - W.S[i];
+    W.S[i] = res;
+    mx = fmax(mx, signed_max ? res : fabs(res));
+  }
+  return block_max(mx, W.red);
+}
+
 // factor + solve + refinement (ldl.cl:602-653); requires W.d, W.RHS set. Leaves dy.
 // CL: the constants of the reference's OpenCL path (preset "cl") are compile-time here -- the
 // branches of the "py" conventions cost the common path registers and issue slots otherwise.
+// Returns true if it leaves w = A' dy (of the final dy) in W.w (residual_free).
 template <bool LS, bool VS, bool CL>
-static __device__ __forceinline__ void solve_normal(const Matrix& A, Work& W, const Params& p) {
+static __device__ __forceinline__ bool solve_normal(const Matrix& A, Work& W, const Params& p, bool free_ok = false) {
   const int m = A.m, tid = threadIdx.x;
   if (!LS && A.tiles) {                     // genuinely sparse factor: tiles of the symbolic pattern only
     solve_normal_tiles(A, W, p);
-    return;
+    return false;
   }
   long long t0 = phase_begin(W);
   const bool refine = p.max_refine > 0;
+  // dense operator with the vectors on chip, iteration in good health (caller): M is not stored, the
+  // residual goes through A (residual_free)
+  const bool matfree = VS && !A.sparse && free_ok;
+  double* const Mst = matfree ? nullptr : W.M;
   if (A.sparse) form_M_sparse(A, W, refine);
   else if (VS)                              // operand staged by TMA, needs the shared work area
     W.ring_g = form_M_dense_tma_call(A.sy_A, A.sy_seg, A.dcols, A.sing_ptr, A.sing_col, A.sing_w, A.m, A.nd,
-                                     A.ldd, A.sy_ldm, A.sy_npass, W.d, W.dg, W.P, W.red, W.L, W.M, W.prof,
+                                     A.ldd, A.sy_ldm, A.sy_npass, W.d, W.dg, W.P, W.red, W.L, Mst, W.prof,
                                      W.ring_g);
   else form_M_dense(A, W);                  // large problems: macro-tile SYRK, 20 KB of staging
   __syncthreads();
@@ -586,6 +644,10 @@ static __device__ __forceinline__ void solve_normal(const Matrix& A, Work& W, co
     if (ahead || big) {          // speculation failed somewhere: restore M and take the exact-capable path
       if (A.sparse && !refine) {
         form_M_sparse(A, W, false);
+      } else if (matfree) {      // (no stored M: form it again)
+        W.ring_g = form_M_dense_tma_call(A.sy_A, A.sy_seg, A.dcols, A.sing_ptr, A.sing_col, A.sing_w, A.m, A.nd,
+                                         A.ldd, A.sy_ldm, A.sy_npass, W.d, W.dg, W.P, W.red, W.L, nullptr, W.prof,
+                                         W.ring_g);
       } else {
         for (int e = tid; e < m * m; e += NT) {
           const int j = e / m, i = e - j * m;
@@ -600,10 +662,10 @@ static __device__ __forceinline__ void solve_normal(const Matrix& A, Work& W, co
   t0 = phase_begin(W);
   back_solve_fast(m, W);
   phase_end(W, 3, t0);
-  if (!refine) return;                                // (nobody would look at the residual)
+  if (!refine) return false;                          // (nobody would look at the residual)
   const bool pymode = !CL && p.refine_mode != 0;      // _ldl.pyx:144-148: signed test, dy -= correction
   t0 = phase_begin(W);
-  double maxr = residual_M(m, W, pymode);
+  double maxr = matfree ? residual_free(A, W, pymode) : residual_M(m, W, pymode);
   phase_end(W, 4, t0);
   int nref = 0;
   while (maxr > p.refine_tol && nref < p.max_refine) {
@@ -612,10 +674,11 @@ static __device__ __forceinline__ void solve_normal(const Matrix& A, Work& W, co
     back_solve_fast(m, W, pymode ? -1.0 : 1.0);
     phase_end(W, 3, t0);
     t0 = phase_begin(W);
-    maxr = residual_M(m, W, pymode);
+    maxr = matfree ? residual_free(A, W, pymode) : residual_M(m, W, pymode);
     phase_end(W, 4, t0);
     nref++;
   }
+  return matfree;
 }
 
 // Given x, z, y (and mu): v = A'y -> W.w ; t, d ; q -> W.w ; RHS ; also rho/sigma norms.
@@ -652,14 +715,15 @@ static __device__ __forceinline__ void prepare_rhs(const Matrix& A, Work& W, dou
 
 // dx, dz, ratio test, update (primal_normal.cl:122-156) using the stored t.  Leaves
 // v = A'y of the UPDATED y in W.t: v_new = (c - t + mu/x) + theta A'dy.
+// have_w: W.w already holds A' dy (left there by residual_free).
 template <bool VS, bool CL>
-static __device__ __forceinline__ void step(const Matrix& A, Work& W, double mu, const Params& p) {
+static __device__ __forceinline__ void step(const Matrix& A, Work& W, double mu, const Params& p, bool have_w = false) {
   const double r = p.r;
   const bool dz1 = !CL && p.dz_mode != 0;
   const bool floor0 = CL || p.theta_floor != 0;
   const int m = A.m, n = A.n, tid = threadIdx.x;
   const double c_first = (tid < n) ? W.c[tid] : 0.0;
-  At_times(A, W.dy, W.w);
+  if (!have_w) At_times(A, W.dy, W.w);
   double th = floor0 ? 0.0 : -INFINITY;          // primal_normal.cl:134 / normal_eqns.py:92
   double big = 0.0;                              // max_j mu / x_j: the cancellation in the carried v
   for (int j = tid; j < n; j += NT) {

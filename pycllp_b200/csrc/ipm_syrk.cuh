@@ -218,8 +218,10 @@ static __device__ __forceinline__ void form_M_dense_tma(const Matrix& A, Work& W
             if (i < m && j <= i) {
               const double v = acc[s][t][h];
               W.L[coff(j, m) + i] = v;
-              W.M[(size_t)i * m + j] = v;
-              W.M[(size_t)j * m + i] = v;
+              if (W.M != nullptr) {                  // (only callers that keep a copy of M for the residual)
+                W.M[(size_t)i * m + j] = v;
+                W.M[(size_t)j * m + i] = v;
+              }
             }
           }
         }
@@ -234,8 +236,8 @@ static __device__ __forceinline__ void form_M_dense_tma(const Matrix& A, Work& W
     if (A.sing_ptr[i + 1] > A.sing_ptr[i]) {
       double s = 0.0;
       for (int e = A.sing_ptr[i]; e < A.sing_ptr[i + 1]; e++) s += A.sing_w[e] * W.d[A.sing_col[e]];
-      const double v = W.M[(size_t)i * m + i] + s;
-      W.M[(size_t)i * m + i] = v;
+      const double v = W.L[coff(i, m) + i] + s;
+      if (W.M != nullptr) W.M[(size_t)i * m + i] = v;
       W.L[coff(i, m) + i] = v;
     }
   }
