@@ -586,9 +586,9 @@ __device__ __forceinline__ void su_t_store(SuCtx& c, int buf, SuT& t) {
   *reinterpret_cast<double2*>(dst + 2) = t.t1;
 }
 
-static __device__ __noinline__ bool factor_ldl_ahead_call(int m, double* L, double* D, double* P, double* red,
-                                                          unsigned long long* prof, double beta, double delta,
-                                                          const double* rhs, double* Sf);
+static __device__ __forceinline__ bool factor_ldl_ahead_call(int m, double* L, double* D, double* P, double* red,
+                                                             unsigned long long* prof, double beta, double delta,
+                                                             const double* rhs, double* Sf);
 
 // Row solve of a 16-row x 64-column unit against the factorised 64x64 diagonal block, in
 // registers, in the accumulator layout of the DMMAs (cx: rows ra+2g, cy: rows ra+2g+1; tile t
@@ -1548,12 +1548,36 @@ static __device__ __forceinline__ bool factor_ldl_ahead(int m, Work& W, double b
 // Out-of-line entry (like the SYRK): inlined into the persistent kernel the chain warp's code is
 // at the mercy of the register allocation of everything around it (measured: +25 % on the 8x8
 // pivot blocks after unrelated code was added to the kernel); as a real function it gets its own.
-static __device__ __noinline__ bool factor_ldl_ahead_call(int m, double* L, double* D, double* P, double* red,
-                                                          unsigned long long* prof, double beta, double delta,
-                                                          const double* rhs, double* Sf) {
+// SH: every pointer is into shared memory.  Generic pointers arriving through the call would make
+// each access a generic LD/ST (ncu: 67 % of the row solve's stall samples on the long scoreboard);
+// re-deriving them from the dynamic shared-memory base lets the compiler emit LDS/STS.
+template <bool SH>
+static __device__ __noinline__ bool factor_ldl_ahead_call_t(int m, double* L, double* D, double* P, double* red,
+                                                            unsigned long long* prof, double beta, double delta,
+                                                            const double* rhs, double* Sf) {
   Work W;
-  W.L = L; W.D = D; W.P = P; W.red = red; W.prof = prof;
+  if (SH) {
+    extern __shared__ __align__(16) double dyn_smem[];
+    const uint32_t b0 = smem_u32(dyn_smem);
+    W.L = dyn_smem + ((smem_u32(L) - b0) >> 3);
+    W.D = dyn_smem + ((smem_u32(D) - b0) >> 3);
+    W.P = dyn_smem + ((smem_u32(P) - b0) >> 3);
+    W.red = dyn_smem + ((smem_u32(red) - b0) >> 3);
+    rhs = dyn_smem + ((smem_u32(rhs) - b0) >> 3);
+    Sf = dyn_smem + ((smem_u32(Sf) - b0) >> 3);
+  } else {
+    W.L = L; W.D = D; W.P = P; W.red = red;
+  }
+  W.prof = prof;
   return factor_ldl_ahead(m, W, beta, delta, rhs, Sf);
+}
+static __device__ __forceinline__ bool factor_ldl_ahead_call(int m, double* L, double* D, double* P, double* red,
+                                                             unsigned long long* prof, double beta, double delta,
+                                                             const double* rhs, double* Sf) {
+  // (block-uniform: D and Sf are in the block's global scratch slot when the vectors do not fit on chip)
+  if (__isShared(D) && __isShared(Sf) && __isShared(rhs))
+    return factor_ldl_ahead_call_t<true>(m, L, D, P, red, prof, beta, delta, rhs, Sf);
+  return factor_ldl_ahead_call_t<false>(m, L, D, P, red, prof, beta, delta, rhs, Sf);
 }
 
 // S <- L^-T S ; dy += S     (second half of ldl.cl:529-536), blocks of 32 columns:

@@ -249,7 +249,8 @@ static __device__ __forceinline__ void form_M_dense_tma(const Matrix& A, Work& W
 // mercy of everything that is live around it (seen: the fragment loads collapse onto one
 // register and serialise, +16 % time); as a real function it gets its own allocation and the
 // caller parks its live values around the single call per Newton step.
-static __device__ __noinline__ int form_M_dense_tma_call(
+template <bool LSH>
+static __device__ __noinline__ int form_M_dense_tma_call_t(
     const double* sy_A, const int4* sy_seg, const int* dcols, const int* sing_ptr, const int* sing_col,
     const double* sing_w, int m, int nd, int ldd, int ldm, int npass, double* d, double* dg, double* P,
     double* red, double* L, double* M, unsigned long long* prof, int ring_g) {
@@ -257,10 +258,29 @@ static __device__ __noinline__ int form_M_dense_tma_call(
   A.m = m; A.nd = nd; A.ldd = ldd; A.sy_ldm = ldm; A.sy_npass = npass;
   A.sy_A = sy_A; A.sy_seg = sy_seg; A.dcols = dcols;
   A.sing_ptr = sing_ptr; A.sing_col = sing_col; A.sing_w = sing_w;
+  // the pointers arrive generic; re-derived from the dynamic shared-memory base they give LDS/STS
+  // (d, dg, the stage area and the reduction scratch are always on chip here; L only if LSH)
+  extern __shared__ __align__(16) double dyn_smem[];
+  const uint32_t b0 = smem_u32(dyn_smem);
   Work W;
-  W.d = d; W.dg = dg; W.P = P; W.red = red; W.L = L; W.M = M; W.prof = prof; W.ring_g = ring_g;
+  W.d = dyn_smem + ((smem_u32(d) - b0) >> 3);
+  W.dg = dyn_smem + ((smem_u32(dg) - b0) >> 3);
+  W.P = dyn_smem + ((smem_u32(P) - b0) >> 3);
+  W.red = dyn_smem + ((smem_u32(red) - b0) >> 3);
+  W.L = LSH ? dyn_smem + ((smem_u32(L) - b0) >> 3) : L;
+  W.M = M; W.prof = prof; W.ring_g = ring_g;
   form_M_dense_tma(A, W);
   return W.ring_g;
+}
+static __device__ __forceinline__ int form_M_dense_tma_call(
+    const double* sy_A, const int4* sy_seg, const int* dcols, const int* sing_ptr, const int* sing_col,
+    const double* sing_w, int m, int nd, int ldd, int ldm, int npass, double* d, double* dg, double* P,
+    double* red, double* L, double* M, unsigned long long* prof, int ring_g) {
+  if (__isShared(L))
+    return form_M_dense_tma_call_t<true>(sy_A, sy_seg, dcols, sing_ptr, sing_col, sing_w, m, nd, ldd, ldm, npass, d,
+                                         dg, P, red, L, M, prof, ring_g);
+  return form_M_dense_tma_call_t<false>(sy_A, sy_seg, dcols, sing_ptr, sing_col, sing_w, m, nd, ldd, ldm, npass, d,
+                                        dg, P, red, L, M, prof, ring_g);
 }
 
 }  // namespace pb200
