@@ -6,8 +6,9 @@
 // synchronisation, and all per-problem state (x, z, y, the normal matrix M, its
 // LDL' factor) stays on-chip / in an L2-resident scratch slot owned by the block.
 //
-// What is computed follows the reference's OpenCL kernels exactly (same
-// constants, same stop rule, same modified LDL', same refinement rule):
+// What is computed follows the reference's OpenCL kernels (same constants, same stop
+// rule, same modified LDL', same refinement rule; the operation ORDER differs -- see the
+// list in DESIGN.md section 1 -- so results agree to rounding, not bit for bit):
 //   primal_normal.cl:201-284  standard_primal_normal          -> ipm_solve_one
 //   primal_normal.cl:30-120   primal/dual infeasibility       -> stage "residual norms"
 //   ldl.cl:110-138,280-294    A (X/Z) A' entries, beta        -> form_M_dense_tma (ipm_syrk.cuh) / form_M_* (once/iteration)
