@@ -1490,6 +1490,17 @@ static __device__ __forceinline__ bool factor_ldl_ahead(int m, Work& W, double b
             old_update16(L, PBcur, m, 0, j1, tg, g, ra, c0, c1, u0, u1);
             sub_unit16(L, m, j2, min(NB, m - j2), ra, g, tg, c0, c1, u0, u1);
           }
+          // ---- the old part of the NEXT table (panel p+3): D_k L(j3+jj, k), k < j1 -- by the twelve
+          // DMMA warps (those without a row unit get to it first), NOT by the three spare warps of
+          // sub-partition 0: anything that runs there takes issue slots and shared-memory bandwidth
+          // from the chain warp (tools/chain_probe.cu: +35 % per panel) ----
+          if (j3 < m) {
+            const int total = j1 * NB;
+            for (int e = widx * 32 + lane; e < total; e += 384) {
+              const int k = e >> 3, jj = e & 7;
+              PBnxt[k * PBS + jj] = (j3 + jj < m) ? L[coff(k, m) + j3 + jj] * D[k] : 0.0;
+            }
+          }
         } else {
           if (warp == 8) {
             // rhs row: Sf[j2+jj] -= sum_{k<j1} Sf[k] table[k][jj]; lane = (k slice, jj)
@@ -1499,14 +1510,6 @@ static __device__ __forceinline__ bool factor_ldl_ahead(int m, Work& W, double b
             acc += __shfl_xor_sync(0xffffffffu, acc, 8);
             acc += __shfl_xor_sync(0xffffffffu, acc, 16);
             if (lane < 8 && j2 + lane < m) Sf[j2 + lane] -= acc;
-          }
-          // ---- the old part of the NEXT table (panel p+3): D_k L(j3+jj, k), k < j1 ----
-          if (j3 < m) {
-            const int total = j1 * NB;
-            for (int e = (warp >> 2) * 32 + lane - 32; e < total; e += 96) {
-              const int k = e >> 3, jj = e & 7;
-              PBnxt[k * PBS + jj] = (j3 + jj < m) ? L[coff(k, m) + j3 + jj] * D[k] : 0.0;
-            }
           }
         }
       }
