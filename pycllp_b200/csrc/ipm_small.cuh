@@ -47,7 +47,7 @@ inline size_t small_smem_doubles(int m, int n, int nd) {
   const int T = (m + 7) / 8, lda = small_lda(nd);
   size_t o = SRED;
   o += (size_t)8 * T * lda;                 // As
-  o += 2 * packed_doubles(m);               // Mp, L
+  o += 2 * al(packed_doubles(m));           // Mp, L (each 16-byte aligned: double2 loads)
   o += al(m + 1);                           // colbuf
   o += 6 * al(n);                           // x z t d w c
   o += 6 * al(m + 1);                       // y b dy S RHS D
@@ -246,24 +246,39 @@ static __device__ __forceinline__ void s_factor(int m, const SmallWork& W, doubl
       const int r = tid;
       const bool live = r >= j0 && r <= m;
       const int jlim = (r < m) ? r - j0 : 7;        // last column of the panel this row has (rhs row: all)
+      const bool spec = !exact && nb == 8;          // (a ragged last panel goes by the sequential rule)
       double c[8];
+      if (!spec) {
 #pragma unroll
-      for (int jj = 0; jj < 8; jj++) {
-        c[jj] = 0.0;
-        if (live && jj < nb && jj <= jlim) c[jj] = (r < m) ? L[W.offs[j0 + jj] + r] : W.S[j0 + jj];
+        for (int jj = 0; jj < 8; jj++) {
+          c[jj] = 0.0;
+          if (live && jj < nb && jj <= jlim) c[jj] = (r < m) ? L[W.offs[j0 + jj] + r] : W.S[j0 + jj];
+        }
       }
       // ---- speculative pass: no communication at all.  Every lane eliminates the 8x8 diagonal
       // block itself (36 entries in registers, D_j = max(|d_j|, delta): the theta term of
       // ldl.cl:368 assumed inactive, as it is for a positive semi-definite M), then solves its own
       // row against the block; theta_j is only accumulated and checked at the end.
       bool bad = false;
-      if (!exact) {
+      if (spec) {
         double e[8][8], rr[8];
+        int ob[8];
 #pragma unroll
-        for (int j = 0; j < 8; j++)
+        for (int j = 0; j < 8; j++) ob[j] = W.offs[j0 + j] + j0;      // (row j0 of column j0 + j; even)
 #pragma unroll
-          for (int i = j; i < 8; i++)
-            e[i][j] = (i < nb) ? L[W.offs[min(j0 + j, m - 1)] + j0 + i] : (i == j ? 1.0 : 0.0);
+        for (int j = 0; j < 8; j++) {
+          if (j & 1) e[j][j] = L[ob[j] + j];
+#pragma unroll
+          for (int i = j + (j & 1); i < 8; i += 2) {                    // 16-byte aligned pairs
+            const double2 v = *reinterpret_cast<const double2*>(L + ob[j] + i);
+            e[i][j] = v.x;
+            e[i + 1][j] = v.y;
+          }
+        }
+        // this thread's row (a row above the panel reads whatever lies there and never uses it)
+        const int ri = r - j0;                      // index inside the panel (rhs row: > 7)
+#pragma unroll
+        for (int jj = 0; jj < 8; jj++) c[jj] = (r < m) ? L[ob[jj] + ri] : W.S[j0 + jj];
 #pragma unroll
         for (int j = 0; j < 8; j++) {
           rr[j] = rcp_pos64(fmax(fabs(e[j][j]), delta));
@@ -274,25 +289,23 @@ static __device__ __forceinline__ void s_factor(int m, const SmallWork& W, doubl
             for (int k = j + 1; k <= i; k++) e[i][k] = fma(-l, e[k][j], e[i][k]);
           }
         }
-        const int ri = r - j0;                      // this row's index inside the panel (rhs row: > 7)
+        const bool below = live && r < m;           // rows that count for theta (not the rhs row)
 #pragma unroll
         for (int k = 0; k < 8; k++) {
-          if (k < nb) {
-            const double Dk = fmax(fabs(e[k][k]), delta);
-            // theta_k over this warp's rows below the pivot; (theta/beta)^2 > D_k would activate the clamp
-            const double th = warp_max_pos((live && ri > k && r < m) ? fabs(c[k]) : 0.0);
-            const double q = th * inv_beta;
-            bad |= !(q * q <= Dk);
-            if (live && ri > k) {
-              const double lk = c[k] * rr[k];
-              c[k] = lk;
+          const double Dk = fmax(fabs(e[k][k]), delta);
+          // (theta_k/beta)^2 > D_k would activate the clamp of ldl.cl:368; theta_k is a maximum over
+          // the rows below the pivot, so it exceeds the threshold iff some row does: no reduction
+          const double q = fabs(c[k]) * inv_beta;
+          bad |= below && ri > k && !(q * q <= Dk);
+          if (live && ri > k) {
+            const double lk = c[k] * rr[k];
+            c[k] = lk;
 #pragma unroll
-              for (int j2 = k + 1; j2 < 8; j2++)
-                if (j2 <= jlim && j2 < nb) c[j2] = fma(-lk, e[j2][k], c[j2]);
-            } else if (ri == k) {
-              c[k] = 1.0;
-              W.D[j0 + k] = Dk;
-            }
+            for (int j2 = k + 1; j2 < 8; j2++)
+              if (j2 <= jlim) c[j2] = fma(-lk, e[j2][k], c[j2]);
+          } else if (ri == k) {
+            c[k] = 1.0;
+            W.D[j0 + k] = Dk;
           }
         }
         // any warp's partial maximum over the threshold <=> the block maximum is
@@ -312,7 +325,7 @@ static __device__ __forceinline__ void s_factor(int m, const SmallWork& W, doubl
           }
         }
       }
-      if (exact || bad) {
+      if (!spec || bad) {
         // ---- the sequential rule, one column at a time with a block-wide theta ----
 #pragma unroll 1
         for (int jj = 0; jj < nb; jj++) {
@@ -581,8 +594,8 @@ ipm_small_kernel(Matrix A, Batch B, Scratch sc, Params p) {
   size_t o = 0;
   W.red = smem + o; o += SRED;
   W.As = smem + o; o += (size_t)8 * W.T * W.lda;
-  W.Mp = smem + o; o += packed_doubles(m);
-  W.L = smem + o; o += packed_doubles(m);
+  W.Mp = smem + o; o += al(packed_doubles(m));
+  W.L = smem + o; o += al(packed_doubles(m));
   W.colbuf = smem + o; o += al(m + 1);
   W.x = smem + o; o += al(n); W.z = smem + o; o += al(n); W.t = smem + o; o += al(n);
   W.d = smem + o; o += al(n); W.w = smem + o; o += al(n); W.c = smem + o; o += al(n);
