@@ -643,6 +643,8 @@ static __device__ __forceinline__ bool solve_normal(const Matrix& A, Work& W, co
   if (big) redo = factor_ldl_big(m, W, beta, p.ldl_delta, W.RHS, W.S);
   if (redo) {
     if (ahead || big) {          // speculation failed somewhere: restore M and take the exact-capable path
+      if (W.prof && tid == 0)    // (counted in a phase slot its path never times: big -> 7, ahead -> 11)
+        reinterpret_cast<unsigned long long*>(W.red + RED_PROF)[big ? 7 : 11] += 1;
       if (A.sparse && !refine) {
         form_M_sparse(A, W, false);
       } else if (matfree) {      // (no stored M: form it again)
