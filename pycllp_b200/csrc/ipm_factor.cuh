@@ -539,7 +539,7 @@ struct SuCtx {
   double* T;
   uint32_t ring;       // shared-memory address of this lane's first ring slot
   double* blk;         // packed nbw x nbw diagonal block (shared memory)
-  double* Wm;          // [64][SB_LDT] k-major: Wm[k][j] = D_k L11[j][k], j > k
+  double* Wm;          // [64][SB_LDT] k-major: Wm[k][j] = -D_k L11[j][k] for j in a later tile than k; diagonal tiles: U_t
   double* rinv;        // [64] 1/D_k
   int* th;             // [64] hi-words of max |c_ik| over the rows below the block
   const Work* W;       // (phase counters)
@@ -592,88 +592,105 @@ static __device__ __forceinline__ bool factor_ldl_ahead_call(int m, double* L, d
 
 // Row solve of a 16-row x 64-column unit against the factorised 64x64 diagonal block, in
 // registers, in the accumulator layout of the DMMAs (cx: rows ra+2g, cy: rows ra+2g+1; tile t
-// holds columns 8t+2tg, 8t+2tg+1), and store of the finished columns.  Same arithmetic as step
-// C of factor_panels, column by column:  l_k = c_k / D_k ;  c_j -= l_k (D_k L11[j][k])  for
-// j > k  -- c_k is broadcast over the four lanes that share a row (one shuffle per row and
-// column), every lane then updates the columns it owns with plain FMAs (16 on average, all
-// independent).  No DMMAs here on purpose: FP64 FMAs queue behind the DMMAs of their SM
-// sub-partition and the warps of a sub-partition are at different columns.
-// The loop over the eight column tiles is NOT unrolled: the finished tile is stored and the
-// others move down one register set, so the body always works on tile 0 (fully unrolled, the
-// 64 columns are 46 KB of code and the warps miss in the instruction cache on every line).
-// WmT[k][j] = D_k L11[j][k] (k-major, row stride SB_LDT: the two columns a lane owns in a tile
-// are one 16-byte word), rinv[k] = 1/D_k.  hmA/hmB: hi-words of max |c_k| over the rows of this
-// warp for column lane / 32+lane (the theta check of the speculative factorisation); vx, vy:
-// row exists; dst: &L(r0, J0 + 2 tg) ; cstep[t]: not needed -- column offsets come from coff.
+// holds columns 8t+2tg, 8t+2tg+1), and store of the finished columns.  Blocked by 8-column tiles,
+// everything on the FP64 tensor pipe:
+//   c_t = b_t U_t           U_t = L11(tile t, tile t)^-T (unit upper triangular 8x8, built once per
+//                           super-panel into the diagonal tiles of the table) -- the unscaled
+//                           entries c_k of the tile's eight columns, all at once;
+//   l_t = c_t / D           the finished columns;
+//   b_j += l_t WmT(t, j)    for the tiles j > t behind it,  WmT[k][j] = -D_k L11[j][k].
+// 4 + 4 (7 - t) DMMAs per tile instead of 64 column steps of a shuffle, a warp reduction, eight
+// 16-byte table loads and 18 FMAs on average: DMMA and DFMA run at the same rate (DESIGN.md
+// section 4), the row solve was bound by its instruction count and the per-column dependency.
+// The accumulator tile becomes the A operand by four shuffles per row tile (entry (g, k) of a
+// C tile lives in lane (g, k >> 1), register k & 1).
+// rinv[k] = 1/D_k.  hmA/hmB: hi-words of max |c_k| over the rows of this warp for column lane /
+// 32+lane (the theta check of the speculative factorisation); vx, vy: row exists.
+__device__ __forceinline__ void c_to_a(double c0, double c1, int sl, bool odd, double& a0, double& a1) {
+  const unsigned FULL = 0xffffffffu;
+  const double p0 = __shfl_sync(FULL, c0, sl), p1 = __shfl_sync(FULL, c1, sl);
+  const double q0 = __shfl_sync(FULL, c0, sl + 2), q1 = __shfl_sync(FULL, c1, sl + 2);
+  a0 = odd ? p1 : p0;
+  a1 = odd ? q1 : q0;
+}
 __device__ __forceinline__ void trsm_unit(double (&cx)[8][2], double (&cy)[8][2],
                                           const double* __restrict__ WmT,
                                           const double* __restrict__ rinv, bool vx, bool vy,
                                           int& hmA, int& hmB, double* __restrict__ L, int m, int J0,
                                           int r0, bool interior) {
   const unsigned FULL = 0xffffffffu;
-  const int lane = threadIdx.x & 31, tg = lane & 3;
-  const int grp = lane & ~3;
-#pragma unroll 1
+  const int lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
+  const int sl = (lane & ~3) | (tg >> 1);            // source lane of A-fragment entry k = tg (k = tg + 4: sl + 2)
+  const bool odd = tg & 1;
+  const bool up = lane & 16;
+  const int hsrc = ((lane & 1) << 4) | ((lane & 7) >> 1);   // a lane that ends up with column lane & 7 of a tile
+  constexpr int KH = 4 * SB_LDT * 8;                 // bytes from table row k to row k + 4
+  constexpr int TD = (8 * SB_LDT + 8) * 8;           // bytes from one diagonal tile of the table to the next
+  const uint32_t wb0 = smem_u32(WmT + tg * SB_LDT + g);
+  const double* rq = rinv + 2 * tg;
+  // (fully unrolled: the tile counts are compile-time -- a predicated-off DMMA costs its full 16
+  // cycles of the pipe, DESIGN.md section 4 -- and no accumulator moves between registers)
+#pragma unroll
   for (int tk = 0; tk < 8; tk++) {
-    const int nt = 7 - tk;                           // tiles behind the current one
-    const uint32_t wb = smem_u32(WmT + (8 * tk) * SB_LDT + 8 * tk + 2 * tg);
-    const double* rv = rinv + 8 * tk;
-    int hm = 0;
+    const uint32_t wb = wb0 + tk * TD;
+    const double u0 = lds_f64(wb), u1 = lds_f64(wb + KH);
+    const double2 rv = *reinterpret_cast<const double2*>(rq + 8 * tk);
+    double a0x, a1x, a0y, a1y;
+    c_to_a(cx[tk][0], cx[tk][1], sl, odd, a0x, a1x);
+    c_to_a(cy[tk][0], cy[tk][1], sl, odd, a0y, a1y);
+    double x0 = 0.0, x1 = 0.0, y0 = 0.0, y1 = 0.0;
+    dmma884(x0, x1, a0x, u0);
+    dmma884(y0, y1, a0y, u0);
+    dmma884(x0, x1, a1x, u1);
+    dmma884(y0, y1, a1y, u1);
+    // theta check: column maxima of |c| over the sixteen rows (three exchange steps: the first
+    // one leaves column 2tg to the lower half-warp and column 2tg+1 to the upper one)
+    {
+      const int h0 = max(vx ? (dbl_hi(x0) & 0x7fffffff) : 0, vy ? (dbl_hi(y0) & 0x7fffffff) : 0);
+      const int h1 = max(vx ? (dbl_hi(x1) & 0x7fffffff) : 0, vy ? (dbl_hi(y1) & 0x7fffffff) : 0);
+      int v = max(up ? h1 : h0, __shfl_xor_sync(FULL, up ? h0 : h1, 16));
+      v = max(v, __shfl_xor_sync(FULL, v, 8));
+      v = max(v, __shfl_xor_sync(FULL, v, 4));
+      const int hm = __shfl_sync(FULL, v, hsrc);
+      // column 8 tk + (lane & 7): lanes 8 (tk & 3) .. +7 of hmA (tk < 4) / hmB
+      if ((lane >> 3) == (tk & 3)) {
+        if (tk < 4) hmA = max(hmA, hm);
+        else hmB = max(hmB, hm);
+      }
+    }
+    x0 *= rv.x; y0 *= rv.x; x1 *= rv.y; y1 *= rv.y;
+    if (tk < 7) {
+      // the tiles behind: b_j += l_t (-WmT)(t, j)
+      c_to_a(x0, x1, sl, odd, a0x, a1x);
+      c_to_a(y0, y1, sl, odd, a0y, a1y);
 #pragma unroll
-    for (int kk = 0; kk < 8; kk++) {
-      const int src = grp | (kk >> 1);
-      const double ckx = __shfl_sync(FULL, cx[0][kk & 1], src);
-      const double cky = __shfl_sync(FULL, cy[0][kk & 1], src);
-      const int hx = vx ? (dbl_hi(ckx) & 0x7fffffff) : 0, hy = vy ? (dbl_hi(cky) & 0x7fffffff) : 0;
-      const int h = __reduce_max_sync(FULL, max(hx, hy));
-      if ((lane & 7) == kk) hm = h;
-      const double r = rv[kk];
-      const double lx = ckx * r, ly = cky * r;
-      // (the table words of four tiles are fetched together, ahead of the branches on nt: a load
-      // inside each branch is one exposed shared-memory round trip per tile and column; words
-      // past the last tile are garbage inside the work area and are not used)
-      double2 w[4];
-      lds_f64x2_x4(wb + 8 * (kk * SB_LDT), w);
-      if (2 * tg > kk) { cx[0][0] = fma(-lx, w[0].x, cx[0][0]); cy[0][0] = fma(-ly, w[0].x, cy[0][0]); }
-      if (2 * tg + 1 > kk) { cx[0][1] = fma(-lx, w[0].y, cx[0][1]); cy[0][1] = fma(-ly, w[0].y, cy[0][1]); }
+      for (int j0 = tk + 1; j0 < 8; j0 += 4) {
+        double b0[4], b1[4];
 #pragma unroll
-      for (int j = 1; j < 4; j++) {
-        if (j <= nt) {
-          cx[j][0] = fma(-lx, w[j].x, cx[j][0]); cy[j][0] = fma(-ly, w[j].x, cy[j][0]);
-          cx[j][1] = fma(-lx, w[j].y, cx[j][1]); cy[j][1] = fma(-ly, w[j].y, cy[j][1]);
+        for (int j = j0; j < j0 + 4 && j < 8; j++) {
+          b0[j - j0] = lds_f64(wb + 64 * (j - tk));
+          b1[j - j0] = lds_f64(wb + KH + 64 * (j - tk));
+        }
+#pragma unroll
+        for (int j = j0; j < j0 + 4 && j < 8; j++) {
+          dmma884(cx[j][0], cx[j][1], a0x, b0[j - j0]);
+          dmma884(cy[j][0], cy[j][1], a0y, b0[j - j0]);
+          dmma884(cx[j][0], cx[j][1], a1x, b1[j - j0]);
+          dmma884(cy[j][0], cy[j][1], a1y, b1[j - j0]);
         }
       }
-      if (nt >= 4) {
-        lds_f64x2_x4(wb + 8 * (kk * SB_LDT + 32), w);
-#pragma unroll
-        for (int j = 4; j < 8; j++) {
-          if (j <= nt) {
-            cx[j][0] = fma(-lx, w[j - 4].x, cx[j][0]); cy[j][0] = fma(-ly, w[j - 4].x, cy[j][0]);
-            cx[j][1] = fma(-lx, w[j - 4].y, cx[j][1]); cy[j][1] = fma(-ly, w[j - 4].y, cy[j][1]);
-          }
-        }
+    }
+    // finished tile -> L
+    {
+      double* q0 = L + coff(J0 + 8 * tk + 2 * tg, m) + r0;
+      double* q1 = L + coff(J0 + 8 * tk + 2 * tg + 1, m) + r0;
+      if (interior) {
+        *reinterpret_cast<double2*>(q0) = make_double2(x0, y0);
+        *reinterpret_cast<double2*>(q1) = make_double2(x1, y1);
+      } else {
+        if (vx) { q0[0] = x0; q1[0] = x1; }
+        if (vy) { q0[1] = y0; q1[1] = y1; }
       }
-      if (tg == (kk >> 1)) { cx[0][kk & 1] = lx; cy[0][kk & 1] = ly; }
-    }
-    // column 8 tk + (lane & 7) of the theta maxima: lanes 8 (tk & 3) .. +7 of hmA (tk < 4) / hmB
-    if ((lane >> 3) == (tk & 3)) {
-      if (tk < 4) hmA = max(hmA, hm);
-      else hmB = max(hmB, hm);
-    }
-    // finished tile -> L, the others move down
-#pragma unroll
-    for (int hh = 0; hh < 2; hh++) {
-      double* q = L + coff(J0 + 8 * tk + 2 * tg + hh, m) + r0;
-      if (interior) *reinterpret_cast<double2*>(q) = make_double2(cx[0][hh], cy[0][hh]);
-      else {
-        if (vx) q[0] = cx[0][hh];
-        if (vy) q[1] = cy[0][hh];
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < 7; j++) {
-      cx[j][0] = cx[j + 1][0]; cx[j][1] = cx[j + 1][1];
-      cy[j][0] = cy[j + 1][0]; cy[j][1] = cy[j + 1][1];
     }
   }
 }
@@ -728,10 +745,16 @@ __device__ __forceinline__ void su_pass(SuCtx& c, int mode, bool active, int ra,
       const int gl = c.g + LA;                       // the chunk to fetch now
       const bool ld = gl < c.gtot;
       if (ld) su_t_load(c, ch + LA >= c.nch ? ch + LA - c.nch : ch + LA, c.rhs && gl < c.nch, tld);
+      // publish chunk g+1.  Look-ahead 1: half-way through the DMMAs (the loads were issued above),
+      // so that the multiplications do not queue behind all of them on the FP64 pipe with the
+      // barrier waiting.  Look-ahead 2 (short chunks): after the DMMAs -- storing before them was
+      // measured slower at config 4, the words then have only one chunk to arrive from HBM.
+      if (LA == 1 && !active && ld) su_t_store(c, c.buf ^ 1, tld);
       if (active) {
         const uint32_t tb = smem_u32(c.T + c.buf * (SB_KCH * SB_LDT) + tg * SB_LDT + col0 + g);
 #pragma unroll
         for (int ks = 0; ks < SB_NST; ks++) {
+          if (LA == 1 && ks == SB_NST / 2 && ld) su_t_store(c, c.buf ^ 1, tld);
           a_issue((ks + SB_NST - 1) % SB_NST);
           const double2 a = an;
           cp_async_wait<SB_NST - 2>();               // the copy of the NEXT k-step has landed
@@ -761,11 +784,7 @@ __device__ __forceinline__ void su_pass(SuCtx& c, int mode, bool active, int ra,
           }
         }
       }
-      if (LA == 1) {
-        if (ld) su_t_store(c, c.buf ^ 1, tld);
-      } else {
-        if (c.g + 1 < c.gtot) su_t_store(c, c.buf ^ 1, tst);
-      }
+      if (LA == 2 && c.g + 1 < c.gtot) su_t_store(c, c.buf ^ 1, tst);
       __syncthreads();
       c.buf ^= 1;
       c.g++;
@@ -989,8 +1008,23 @@ static __device__ __noinline__ bool super_panel(int m, int J0, int nbw, Work& W,
     if (ib >= jb) {
       const double l = c.blk[packed_off(jb, nbw) + ib];
       c.L[coff(J0 + jb, m) + J0 + ib] = l;
-      if (ib > jb) c.Wm[jb * SB_LDT + ib] = l * W.D[J0 + jb];
+      if ((ib >> 3) > (jb >> 3)) c.Wm[jb * SB_LDT + ib] = -(l * W.D[J0 + jb]);
     }
+  }
+  // the diagonal tiles of the table: U_t = L11(tile t, tile t)^-T for the row solve (trsm_unit);
+  // thread (t, j) solves column j of the inverse = row j of U_t
+  if (nbw == SB && tid < SB) {
+    const int t8 = tid & ~7, j = tid & 7;
+    double v[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      double s = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k = 0; k < i; k++) s = fma(-c.blk[packed_off(t8 + k, nbw) + t8 + i], v[k], s);
+      v[i] = s;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) c.Wm[(t8 + j) * SB_LDT + t8 + i] = v[i];
   }
   if (tid < nbw) c.rinv[tid] = 1.0 / W.D[J0 + tid];
   __syncthreads();
