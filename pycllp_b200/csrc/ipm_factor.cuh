@@ -696,6 +696,7 @@ __device__ __forceinline__ void trsm_unit(double (&cx)[8][2], double (&cy)[8][2]
 }
 
 // What a pass does with its accumulators.
+constexpr int SU_ITEM = 4;  // column tiles of an item of step 1 (2: 16x16, look-ahead 2 for T; 4: 16x32, half the operand bytes per DMMA)
 constexpr int SU_RMW = 0;    // 16x16 item below the diagonal block: panel -= acc (global)
 constexpr int SU_DIAG = 1;   // 16x16 item of the diagonal block: (panel - acc) -> shared-memory block
 constexpr int SU_TRSM = 2;   // 16x64 unit below the diagonal block: (panel - acc), row solve, -> global
@@ -947,32 +948,39 @@ static __device__ __noinline__ bool super_panel(int m, int J0, int nbw, Work& W,
   const int nbelow = (m - J0 - nbw + 15) >> 4;       // 16-row units below the diagonal block
   const int nfull = nbelow >> 4, rem = nbelow & 15;
   const int nru = (nbw + 15) >> 4;                   // row units of the diagonal block
-  const int ndiag = nru * (nru + 1) / 2;             // its items on or below the diagonal
+  // items of the diagonal block on or below the diagonal: 16 rows x (8 SU_ITEM) columns each
+  const int ndiag = SU_ITEM == 2 ? nru * (nru + 1) / 2 : nru + (nru > 2 ? nru - 2 : 0);
   // (the diagonal items must all sit in the LAST pass -- their epilogue overwrites the T buffers --
   // so the left-over items are padded to a full pass when the two kinds would straddle one)
-  int nrmw = kloop ? 4 * rem : 0;
+  constexpr int IPU = 8 / SU_ITEM;                   // items per 16-row unit
+  int nrmw = kloop ? IPU * rem : 0;
   if ((nrmw & (NWARP - 1)) + ndiag > NWARP) nrmw = (nrmw + NWARP - 1) & ~(NWARP - 1);
   const int nit = nrmw + ndiag;
   const int nq = (nit + NWARP - 1) / NWARP;
   if (tid < SB) c.th[tid] = 0;
   long long t0 = phase_begin(W);
-  // ---- 1. 16x16 items ----
-  if (kloop) su_t_prime(c, nq, 2, true);
+  // ---- 1. 16 x (8 SU_ITEM) items ----
+  if (kloop) su_t_prime(c, nq, SU_ITEM == 2 ? 2 : 1, true);
   for (int q = 0; q < nq; q++) {
     const int it = q * NWARP + warp;
     // item order: left-over units first, diagonal block LAST (its epilogue overwrites T)
     const int id = it - (nit - ndiag);               // index among the diagonal items
     int mode = SU_RMW, ru, cg;
-    bool active = it < nit && (id >= 0 || it < 4 * rem);
+    bool active = it < nit && (id >= 0 || it < IPU * rem);
     if (id >= 0) {
       mode = SU_DIAG;
-      ru = (id >= 6) ? 3 : (id >= 3) ? 2 : (id >= 1) ? 1 : 0;
-      cg = id - ru * (ru + 1) / 2;
+      if (SU_ITEM == 2) {
+        ru = (id >= 6) ? 3 : (id >= 3) ? 2 : (id >= 1) ? 1 : 0;
+        cg = id - ru * (ru + 1) / 2;
+      } else {                                       // row units 0, 1: one item; 2, 3: two
+        ru = id < 2 ? id : 2 + ((id - 2) >> 1);
+        cg = id < 2 ? 0 : (id - 2) & 1;
+      }
     } else {
-      ru = 4 + (it >> 2);                            // (below the diagonal block: nbw == 64)
-      cg = it & 3;
+      ru = 4 + it / IPU;                             // (below the diagonal block: nbw == 64)
+      cg = it % IPU;
     }
-    su_pass<2>(c, mode, active, J0 + 16 * ru, 16 * cg, kloop);
+    su_pass<SU_ITEM>(c, mode, active, J0 + 16 * ru, 8 * SU_ITEM * cg, kloop);
   }
   __syncthreads();
   phase_end(W, 14, t0);
