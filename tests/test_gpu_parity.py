@@ -324,6 +324,26 @@ def test_large_problems_out_of_shared_memory(engine, oracle):
     _check_optimality(As.tocsr(), b, c, rs, "sparse m=1100")
 
 
+def test_super_panel_factor_shape_sweep(engine, oracle):
+    """The factor in global memory (m > ~202: 64-column super-panels, 16x32 items, row solve of the
+    16x64 units on the tensor pipe against the inverted 8x8 diagonal tiles) over its boundaries:
+    ragged last row unit, ragged last super-panel, with and without a full pass of sixteen units,
+    odd m.  No refinement on the sparse solver (ldl.cl:698-711), so an error of the factorisation
+    shows up as a different step count."""
+    rng = np.random.RandomState(23)
+    for m in (209, 256, 271, 300, 337, 577):
+        n0, N = m // 3 + 1, 2
+        A = np.c_[rng.rand(m, n0), np.eye(m)]
+        b = 0.5 + rng.rand(N, m)
+        c = np.c_[0.5 + rng.rand(N, n0), np.zeros((N, m))]
+        ref = oracle.solve_sparse(A, b, c)
+        res = _sparse(engine, A, b, c)
+        assert not engine.info()["factor_in_smem"]
+        assert_parity(res, ref, c, "sparse, dense A, m=%d" % m)
+        np.testing.assert_array_equal(res["iters"], ref.iters, err_msg="m=%d" % m)
+        assert_parity(_dense(engine, A, b, c), oracle.solve_dense(A, b, c), c, "dense m=%d" % m)
+
+
 def test_config4_at_its_named_shape_vs_reference_golden(engine):
     """Config 4 exactly as BASELINE.json names it (m=2000, n=5000, 1 % density + slacks): the
     first two LPs of the 1024-LP seed-0 workload against the outputs of the REFERENCE's own
