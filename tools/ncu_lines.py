@@ -1,6 +1,9 @@
 """Join an ncu SASS source page (csv) with nvdisasm line info -> stall samples per source line.
 
 usage: ncu_lines.py <report.ncu-rep> <lib.so> [kernel-substring] [top]
+
+The kernel substring must select ONE instance of the mangled name (e.g. ipm_solve_kernelILb1ELb1ELb1ELi1:
+the two-blocks-per-SM build in ipm_kernels_small.cu carries ...ELi2 and would shadow it).
 """
 import csv, io, os, re, subprocess, sys, tempfile, collections
 
