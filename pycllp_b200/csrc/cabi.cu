@@ -615,9 +615,11 @@ static int setup_sparse_impl(pycllp_b200_engine* e, int m, int n, const int* ind
     for (int a = Tp[k]; a < Tp[k + 1]; a++)
       for (int b2 = Tp[k]; b2 <= a; b2++)
         tr.push_back({Ti[a], Ti[b2], k, Tx[a] * Tx[b2]});
+  // entries in the order of the packed column-major factor storage (column j, then row i): the
+  // threads of a warp then write neighbouring addresses in form_M_sparse; terms by ascending k
   std::sort(tr.begin(), tr.end(), [](const Tr& u, const Tr& v) {
-    if (u.i != v.i) return u.i < v.i;
     if (u.j != v.j) return u.j < v.j;
+    if (u.i != v.i) return u.i < v.i;
     return u.k < v.k;
   });
   std::vector<int> me_ptr, me_i, me_j, mt_k;
