@@ -430,28 +430,29 @@ static __device__ __forceinline__ void form_M_sparse(const Matrix& A, Work& W, b
     for (size_t e = threadIdx.x; e < n2; e += NT) L2[e] = make_double2(0.0, 0.0);
   }
   __syncthreads();
-  // FQ entries per thread and round, their dependent loads (list bounds -> k -> d_k) issued
+  // four entries per thread and round, their dependent loads (list bounds -> k -> d_k) issued
   // side by side: one entry at a time is three serialised L2 round trips per entry.  The entries
   // come in the order of the packed storage (cabi.cu), so a warp writes neighbouring addresses.
-  constexpr int FQ = 8;
-  for (int e0 = threadIdx.x; e0 < A.nme; e0 += FQ * NT) {
-    int t0[FQ], t1[FQ], i[FQ], j[FQ], k[FQ];
-    double w[FQ], s[FQ];
+  // (eight per round: 7 % less at config 4 -- and the untouched SYRK of the same build 13 % slower at
+  // config 3, DESIGN.md section 6 on the code generator; not kept)
+  for (int e0 = threadIdx.x; e0 < A.nme; e0 += 4 * NT) {
+    int t0[4], t1[4], i[4], j[4], k[4];
+    double w[4], s[4];
 #pragma unroll
-    for (int q = 0; q < FQ; q++) {
+    for (int q = 0; q < 4; q++) {
       const int e = min(e0 + q * NT, A.nme - 1);
       t0[q] = A.me_ptr[e]; t1[q] = A.me_ptr[e + 1];
       i[q] = A.me_i[e]; j[q] = A.me_j[e];
     }
 #pragma unroll
-    for (int q = 0; q < FQ; q++) { k[q] = A.mt_k[t0[q]]; w[q] = A.mt_w[t0[q]]; }   // every entry has >= 1 term
+    for (int q = 0; q < 4; q++) { k[q] = A.mt_k[t0[q]]; w[q] = A.mt_w[t0[q]]; }   // every entry has >= 1 term
 #pragma unroll
-    for (int q = 0; q < FQ; q++) s[q] = w[q] * W.d[k[q]];
+    for (int q = 0; q < 4; q++) s[q] = w[q] * W.d[k[q]];
 #pragma unroll
-    for (int q = 0; q < FQ; q++)
+    for (int q = 0; q < 4; q++)
       for (int t = t0[q] + 1; t < t1[q]; t++) s[q] += A.mt_w[t] * W.d[A.mt_k[t]];
 #pragma unroll
-    for (int q = 0; q < FQ; q++) {
+    for (int q = 0; q < 4; q++) {
       if (e0 + q * NT < A.nme) {
         W.L[cidx(i[q], j[q], m)] = s[q];
         if (keepM) {
