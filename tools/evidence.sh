@@ -30,4 +30,6 @@ python tests/tools/gpu_check.py prof5 > $O/phase_cfg5.txt 2>&1
 python tests/tools/gpu_check.py prof4 > $O/phase_cfg4.txt 2>&1
 python tests/tools/gpu_check.py proft > $O/phase_stair.txt 2>&1
 PB200_SMALL=3 python tests/tools/gpu_check.py prof1 prof1s > $O/phase_cfg1.txt 2>&1
+# (read the report HERE, not on the box:  python tools/ncu_summary.py $O/prof_cfg3.ncu-rep pycllp_b200/libpycllp_b200.so \
+#    "<note>" ipm_solve_kernelILb1ELb1ELb1ELi1 > profiles/ncu_summary_$TAG.txt ;  python tools/sass_hist.py > profiles/sass_r02.txt)
 ls -la $O
