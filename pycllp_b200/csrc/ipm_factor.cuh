@@ -746,6 +746,13 @@ __device__ __forceinline__ void su_pass(SuCtx& c, int mode, bool active, int ra,
       const int gl = c.g + LA;                       // the chunk to fetch now
       const bool ld = gl < c.gtot;
       if (ld) su_t_load(c, ch + LA >= c.nch ? ch + LA - c.nch : ch + LA, c.rhs && gl < c.nch, tld);
+      if (NCT == 8 && active && ch == c.nch - 1) {
+        // the panel entries this unit reads right after its K-loop (64 columns x 128 bytes): into
+        // L2 during the last chunk, two lines per lane (config 4 streams them from HBM)
+        const double* q = c.L + ra;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(q + coff(J0 + 2 * lane, m)));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(q + coff(J0 + 2 * lane + 1, m)));
+      }
       // publish chunk g+1.  Look-ahead 1: half-way through the DMMAs (the loads were issued above),
       // so that the multiplications do not queue behind all of them on the FP64 pipe with the
       // barrier waiting.  Look-ahead 2 (short chunks): after the DMMAs -- storing before them was
