@@ -488,9 +488,10 @@ static __device__ __forceinline__ void factor_ldl_fast(int m, Work& W, double be
 //     shared memory (row stride 68 = 4 mod 16: conflict-free B fragments), one __syncthreads per
 //     chunk; the global loads of the next chunk are issued before the DMMAs of the current one;
 //   * the rows of a super-panel are processed in passes of 16 units (256 rows); what is left over
-//     (and the diagonal block) goes as 16x16 items, four warps per row unit, so that partial
-//     passes still use all warps; the right-hand-side row (Sf, kept in place) is accumulated by
-//     the threads that build T, four FMAs per chunk each.
+//     (and the diagonal block) goes as 16x32 items (SU_ITEM), two warps per row unit, so that
+//     partial passes still use all warps -- 16x16 items, four warps per unit, were bound by the
+//     operand stream from L2, not by the DMMAs; the right-hand-side row (Sf, kept in place) is
+//     accumulated by the threads that build T, four FMAs per chunk each.
 // Per k-step a warp issues 16 DMMAs for 512 bytes of L: 8 B/cycle per SM at the DMMA rate,
 // well under the 20-35 B/cycle an SM gets from L2.
 // ---------------------------------------------------------------------------------------
@@ -926,14 +927,15 @@ __device__ __forceinline__ void su_t_prime(SuCtx& c, int npass, int LA, bool rhs
 
 // One super-panel (columns J0 .. J0+nbw-1) of factor_ldl_big.  Returns (block-uniform) true if
 // the speculation "theta clamp inactive" could not be proven for one of its columns.
-//   1. K-loop passes of 16x16 items: the left-over row units below the diagonal block (those that
+//   1. K-loop passes of 16x32 items: the left-over row units below the diagonal block (those that
 //      do not fill a pass of sixteen 16x64 units; panel -= acc in global memory) and, in the last
 //      of these passes, the items of the diagonal block, which land in shared memory;
 //   2. the right-hand-side row (accumulated by the T-build threads) is reduced, the nbw x nbw
 //      diagonal block is factorised in shared memory by factor_panels (right-hand side riding
-//      along), written to L, and the row-solve tables Wm = D_k L11[j][k], 1/D_k are built;
+//      along), written to L, and the row-solve tables are built: Wm = -D_k L11[j][k] for j in a
+//      later 8-column tile than k, the inverted diagonal tiles U_t in the diagonal tiles, 1/D_k;
 //   3. full passes of sixteen 16x64 units below the diagonal block: K-loop, then the row solve
-//      against the diagonal block in registers (trsm_unit) -- each entry of the panel is read
+//      against the diagonal block in registers (trsm_unit, on the tensor pipe) -- each entry of the panel is read
 //      once and written once; the left-over units of step 1 get their row solve last.
 static __device__ __noinline__ bool super_panel(int m, int J0, int nbw, Work& W, double beta, double delta,
                                                 double* Sf) {
