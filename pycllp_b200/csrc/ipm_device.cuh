@@ -666,7 +666,7 @@ static __device__ __forceinline__ bool solve_normal(const Matrix& A, Work& W, co
   }
   phase_end(W, 2, t0);
   t0 = phase_begin(W);
-  back_solve_fast(m, W);
+  back_solve_fast<!LS>(m, W);
   phase_end(W, 3, t0);
   if (!refine) return false;                          // (nobody would look at the residual)
   const bool pymode = !CL && p.refine_mode != 0;      // _ldl.pyx:144-148: signed test, dy -= correction
@@ -677,7 +677,7 @@ static __device__ __forceinline__ bool solve_normal(const Matrix& A, Work& W, co
   while (maxr > p.refine_tol && nref < p.max_refine) {
     t0 = phase_begin(W);
     fwd_solve_fast(m, W);
-    back_solve_fast(m, W, pymode ? -1.0 : 1.0);
+    back_solve_fast<!LS>(m, W, pymode ? -1.0 : 1.0);
     phase_end(W, 3, t0);
     t0 = phase_begin(W);
     maxr = matfree ? residual_free(A, W, pymode) : residual_M(m, W, pymode);

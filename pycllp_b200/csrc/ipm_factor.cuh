@@ -1637,6 +1637,9 @@ static __device__ __forceinline__ bool factor_ldl_ahead_call(int m, double* L, d
 // S <- L^-T S ; dy += S     (second half of ldl.cl:529-536), blocks of 32 columns:
 // the part of each dot product below the block is a warp-per-column reduction on all
 // warps, the 32x32 triangle is back-substituted by warp 0 in registers with shuffles.
+// GLOB: L lives in global memory (a load is an L2 / HBM round trip): the two columns of a warp
+// together, four loads each in flight, instead of one load per loop iteration.
+template <bool GLOB = false>
 static __device__ __forceinline__ void back_solve_fast(int m, Work& W, double sign = 1.0) {
   const int tid = threadIdx.x, lane = tid & 31, warp = warp_id();
   const double* __restrict__ L = W.L;
@@ -1646,12 +1649,37 @@ static __device__ __forceinline__ void back_solve_fast(int m, Work& W, double si
     const int c0 = kb << 5;
     const int c1 = min(m, c0 + 32);
     if (c1 < m) {
-      for (int j = c0 + warp; j < c1; j += NWARP) {
-        const double* col = L + cidx(j, j, m) - j;     // col[i] = L(i, j)
-        double acc = 0.0;
-        for (int i = c1 + lane; i < m; i += 32) acc += col[i] * S[i];
-        acc = warp_sum(acc);
-        if (lane == 0) S[j] -= acc;
+      if constexpr (GLOB) {
+        const int ja = c0 + warp, jb = ja + NWARP;     // (ja < c1: a block below the last one is full)
+        const bool hb = jb < c1;
+        const double* ca = L + cidx(ja, ja, m) - ja;   // ca[i] = L(i, ja)
+        const double* cb = hb ? L + cidx(jb, jb, m) - jb : ca;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
+        int i = c1 + lane;
+        for (; i + 96 < m; i += 128) {
+          const double la0 = ca[i], la1 = ca[i + 32], la2 = ca[i + 64], la3 = ca[i + 96];
+          const double lb0 = cb[i], lb1 = cb[i + 32], lb2 = cb[i + 64], lb3 = cb[i + 96];
+          const double s0 = S[i], s1 = S[i + 32], s2 = S[i + 64], s3 = S[i + 96];
+          a0 = fma(la0, s0, a0); a1 = fma(la1, s1, a1); a2 = fma(la2, s2, a2); a3 = fma(la3, s3, a3);
+          b0 = fma(lb0, s0, b0); b1 = fma(lb1, s1, b1); b2 = fma(lb2, s2, b2); b3 = fma(lb3, s3, b3);
+        }
+        for (; i < m; i += 32) {
+          const double la = ca[i], lb = cb[i], si = S[i];
+          a0 = fma(la, si, a0); b0 = fma(lb, si, b0);
+        }
+        const double sa = warp_sum((a0 + a1) + (a2 + a3)), sb = warp_sum((b0 + b1) + (b2 + b3));
+        if (lane == 0) {
+          if (ja < c1) S[ja] -= sa;
+          if (hb) S[jb] -= sb;
+        }
+      } else {
+        for (int j = c0 + warp; j < c1; j += NWARP) {
+          const double* col = L + cidx(j, j, m) - j;     // col[i] = L(i, j)
+          double acc = 0.0;
+          for (int i = c1 + lane; i < m; i += 32) acc += col[i] * S[i];
+          acc = warp_sum(acc);
+          if (lane == 0) S[j] -= acc;
+        }
       }
       __syncthreads();
     }
