@@ -422,6 +422,7 @@ static __device__ __forceinline__ void form_M_dense(const Matrix& A, Work& W) {
 // lists, straight into the packed factor storage, which is cleared first (the factorisation of
 // the previous step left its fill there).  keepM: also into the full symmetric M for the
 // refinement residual (the reference's sparse path has none, ldl.cl:698-711).
+template <int FQ = 4>
 static __device__ __forceinline__ void form_M_sparse(const Matrix& A, Work& W, bool keepM) {
   const int m = A.m;
   {
@@ -430,29 +431,30 @@ static __device__ __forceinline__ void form_M_sparse(const Matrix& A, Work& W, b
     for (size_t e = threadIdx.x; e < n2; e += NT) L2[e] = make_double2(0.0, 0.0);
   }
   __syncthreads();
-  // four entries per thread and round, their dependent loads (list bounds -> k -> d_k) issued
+  // FQ entries per thread and round (four in the shared-memory kernel, eight with the factor in
+  // global memory), their dependent loads (list bounds -> k -> d_k) issued
   // side by side: one entry at a time is three serialised L2 round trips per entry.  The entries
   // come in the order of the packed storage (cabi.cu), so a warp writes neighbouring addresses.
-  // (eight per round: 7 % less at config 4 -- and the untouched SYRK of the same build 13 % slower at
-  // config 3, DESIGN.md section 6 on the code generator; not kept)
-  for (int e0 = threadIdx.x; e0 < A.nme; e0 += 4 * NT) {
-    int t0[4], t1[4], i[4], j[4], k[4];
-    double w[4], s[4];
+  // (eight per round in the shared-memory kernel as well made the untouched SYRK of that kernel 13 %
+  // slower, DESIGN.md section 6 on the code generator: its instance stays at four)
+  for (int e0 = threadIdx.x; e0 < A.nme; e0 += FQ * NT) {
+    int t0[FQ], t1[FQ], i[FQ], j[FQ], k[FQ];
+    double w[FQ], s[FQ];
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
+    for (int q = 0; q < FQ; q++) {
       const int e = min(e0 + q * NT, A.nme - 1);
       t0[q] = A.me_ptr[e]; t1[q] = A.me_ptr[e + 1];
       i[q] = A.me_i[e]; j[q] = A.me_j[e];
     }
 #pragma unroll
-    for (int q = 0; q < 4; q++) { k[q] = A.mt_k[t0[q]]; w[q] = A.mt_w[t0[q]]; }   // every entry has >= 1 term
+    for (int q = 0; q < FQ; q++) { k[q] = A.mt_k[t0[q]]; w[q] = A.mt_w[t0[q]]; }   // every entry has >= 1 term
 #pragma unroll
-    for (int q = 0; q < 4; q++) s[q] = w[q] * W.d[k[q]];
+    for (int q = 0; q < FQ; q++) s[q] = w[q] * W.d[k[q]];
 #pragma unroll
-    for (int q = 0; q < 4; q++)
+    for (int q = 0; q < FQ; q++)
       for (int t = t0[q] + 1; t < t1[q]; t++) s[q] += A.mt_w[t] * W.d[A.mt_k[t]];
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
+    for (int q = 0; q < FQ; q++) {
       if (e0 + q * NT < A.nme) {
         W.L[cidx(i[q], j[q], m)] = s[q];
         if (keepM) {
@@ -604,7 +606,7 @@ static __device__ __forceinline__ bool solve_normal(const Matrix& A, Work& W, co
   // residual goes through A (residual_free)
   const bool matfree = VS && !A.sparse && free_ok;
   double* const Mst = matfree ? nullptr : W.M;
-  if (A.sparse) form_M_sparse(A, W, refine);
+  if (A.sparse) form_M_sparse<LS ? 4 : 8>(A, W, refine);
   else if (VS)                              // operand staged by TMA, needs the shared work area
     W.ring_g = form_M_dense_tma_call(A.sy_A, A.sy_seg, A.dcols, A.sing_ptr, A.sing_col, A.sing_w, A.m, A.nd,
                                      A.ldd, A.sy_ldm, A.sy_npass, W.d, W.dg, W.P, W.red, W.L, Mst, W.prof,
@@ -649,7 +651,7 @@ static __device__ __forceinline__ bool solve_normal(const Matrix& A, Work& W, co
       if (W.prof && tid == 0)    // (counted in a phase slot its path never times: big -> 7, ahead -> 11)
         reinterpret_cast<unsigned long long*>(W.red + RED_PROF)[big ? 7 : 11] += 1;
       if (A.sparse && !refine) {
-        form_M_sparse(A, W, false);
+        form_M_sparse<LS ? 4 : 8>(A, W, false);
       } else if (matfree) {      // (no stored M: form it again)
         W.ring_g = form_M_dense_tma_call(A.sy_A, A.sy_seg, A.dcols, A.sing_ptr, A.sing_col, A.sing_w, A.m, A.nd,
                                          A.ldd, A.sy_ldm, A.sy_npass, W.d, W.dg, W.P, W.red, W.L, nullptr, W.prof,
