@@ -1656,6 +1656,7 @@ static __device__ __forceinline__ void back_solve_fast(int m, Work& W, double si
         const double* cb = hb ? L + cidx(jb, jb, m) - jb : ca;
         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
         int i = c1 + lane;
+#pragma unroll 2
         for (; i + 96 < m; i += 128) {
           const double la0 = ca[i], la1 = ca[i + 32], la2 = ca[i + 64], la3 = ca[i + 96];
           const double lb0 = cb[i], lb1 = cb[i + 32], lb2 = cb[i + 64], lb3 = cb[i + 96];
